@@ -1,0 +1,116 @@
+"""ctypes binding of libdcora_b200.so (the C-ABI in include/dcora_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcora_b200.so")
+
+c_int32_p = C.POINTER(C.c_int32)
+c_double_p = C.POINTER(C.c_double)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+
+class AgentDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("l", C.c_int32), ("b", C.c_int32),
+                ("rowptr", c_int32_p), ("col", c_int32_p), ("val", c_double_p),
+                ("G", c_double_p), ("precond_reg", C.c_double)]
+
+
+class ROptParams(C.Structure):
+    _fields_ = [("method", C.c_int32), ("verbose", C.c_int32),
+                ("gradnorm_tol", C.c_double), ("RGD_stepsize", C.c_double),
+                ("RGD_use_preconditioner", C.c_int32), ("RTR_iterations", C.c_int32),
+                ("RTR_tCG_iterations", C.c_int32), ("RTR_initial_radius", C.c_double),
+                ("time_bound_s", C.c_double), ("retraction", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ROptResult(C.Structure):
+    _fields_ = [("success", C.c_int32), ("tCGStatus", C.c_int32),
+                ("fInit", C.c_double), ("gradNormInit", C.c_double),
+                ("fOpt", C.c_double), ("gradNormOpt", C.c_double),
+                ("elapsedMs", C.c_double), ("outer_iterations", C.c_int32),
+                ("inner_iterations", C.c_int32), ("accepted", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class CertifyResult(C.Structure):
+    _fields_ = [("is_psd", C.c_int32), ("converged", C.c_int32),
+                ("matvecs", C.c_int32), ("restarts", C.c_int32),
+                ("lambda_min", C.c_double), ("theta", C.c_double),
+                ("residual", C.c_double)]
+
+
+# every symbol include/dcora_b200.h declares: name -> (restype, argtypes)
+VP = C.c_void_p
+SYMBOLS = {
+    "dcora_ropt_params_default": (None, [C.POINTER(ROptParams)]),
+    "dcora_last_error": (C.c_char_p, []),
+    "dcora_device_count": (C.c_int, []),
+    "dcora_problem_create": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(VP)]),
+    "dcora_problem_destroy": (None, [VP]),
+    "dcora_problem_clone_rank": (C.c_int, [VP, C.c_int32, C.POINTER(VP)]),
+    "dcora_problem_dim": (C.c_int64, [VP]),
+    "dcora_problem_rank": (C.c_int32, [VP]),
+    "dcora_problem_num_agents": (C.c_int32, [VP]),
+    "dcora_problem_nnz": (C.c_int64, [VP]),
+    "dcora_problem_factor_nnz": (C.c_int64, [VP]),
+    "dcora_problem_stream": (VP, [VP]),
+    "dcora_problem_launch_count": (C.c_int64, [VP]),
+    "dcora_problem_set_G": (C.c_int, [VP, VP]),
+    "dcora_problem_f": (C.c_int, [VP, VP, c_double_p]),
+    "dcora_problem_egrad": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_hessvec": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_precond": (C.c_int, [VP, VP, VP, VP]),
+    "dcora_problem_rgrad": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_rgradnorm": (C.c_int, [VP, VP, c_double_p]),
+    "dcora_problem_retract": (C.c_int, [VP, VP, VP, VP, C.c_int32]),
+    "dcora_problem_project_tangent": (C.c_int, [VP, VP, VP, VP]),
+    "dcora_problem_project_manifold": (C.c_int, [VP, VP, VP]),
+    "dcora_rtr_solve": (C.c_int, [VP, VP, VP, C.POINTER(ROptParams), c_uint8_p,
+                                  C.POINTER(ROptResult)]),
+    "dcora_certify": (C.c_int, [VP, VP, C.c_double, C.c_int32, C.c_double,
+                                C.POINTER(CertifyResult), VP]),
+    "dcora_problem_escape_saddle": (C.c_int, [VP, VP, C.c_double, VP, C.c_double,
+                                              C.c_double, C.c_int32, C.c_int32, VP]),
+    "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
+    "dcora_selfcheck_layout": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, c_double_p]),
+    "dcora_selfcheck_cholesky": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,
+                                           C.c_int32, C.c_int32, C.c_double, c_double_p,
+                                           C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+class DcoraError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DcoraError(
+            f"{LIB_PATH} is missing: build it with `python -m dcora_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc < 0:
+        raise DcoraError(f"dcora_b200 error {rc}: {load().dcora_last_error().decode()}")
+    return rc

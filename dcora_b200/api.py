@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference interface for the hot path, over the C-ABI.
+
+Names and argument meaning follow DCORA::QuadraticProblem
+(include/DCORA/QuadraticProblem.h:44-185), DCORA::QuadraticOptimizer
+(include/DCORA/QuadraticOptimizer.h:30-120), ROptParameters / ROPTResult
+(include/DCORA/DCORA_types.h:152-233) and the certification free functions
+(include/DCORA/DCORA_utils.h:224-292).  Nothing here computes: every method is
+one call into libdcora_b200.so, which runs on the GPU or fails.
+
+Matrices are numpy arrays of shape (r, K) (any memory order; copied to the
+column-major layout the reference uses) or CUDA torch tensors of shape (K, r),
+contiguous -- the same bytes, already resident in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import AgentDesc, CertifyResult, ROptParams, ROptResult, check
+
+ORDER_SE, ORDER_RA = 0, 1
+RETRACT_QF, RETRACT_POLAR = 0, 1
+TCG_STATUS = ["TR_NEGCURVTURE", "TR_EXCREGION", "TR_LCON", "TR_SCON", "TR_MAXITER"]
+
+
+@dataclass
+class AgentData:
+    """What Graph hands to QuadraticProblem for one agent: Q (scipy CSR or
+    (rowptr, col, val)), optional G (r x k), n / l / b and the preconditioner
+    regularisation (None disables the Cholesky preconditioner)."""
+    n: int
+    Q: object
+    l: int = 0
+    b: int = 0
+    G: np.ndarray | None = None
+    precond_reg: float | None = 0.1
+
+
+@dataclass
+class ROptParameters:
+    method: str = "RTR"
+    verbose: bool = False
+    gradnorm_tol: float = 1e-2
+    RGD_stepsize: float = 1e-3
+    RGD_use_preconditioner: bool = True
+    RTR_iterations: int = 3
+    RTR_tCG_iterations: int = 50
+    RTR_initial_radius: float = 100.0
+    time_bound_s: float = 5.0      # QuadraticOptimizer.cpp:252; <=0 disables
+    retraction: int = RETRACT_QF
+
+    def to_c(self):
+        p = ROptParams()
+        p.method = 0 if self.method == "RTR" else 1
+        p.verbose = int(self.verbose)
+        p.gradnorm_tol = self.gradnorm_tol
+        p.RGD_stepsize = self.RGD_stepsize
+        p.RGD_use_preconditioner = int(self.RGD_use_preconditioner)
+        p.RTR_iterations = self.RTR_iterations
+        p.RTR_tCG_iterations = self.RTR_tCG_iterations
+        p.RTR_initial_radius = self.RTR_initial_radius
+        p.time_bound_s = self.time_bound_s
+        p.retraction = self.retraction
+        return p
+
+
+@dataclass
+class ROPTResult:
+    success: bool = False
+    fInit: float = 0.0
+    gradNormInit: float = 0.0
+    fOpt: float = 0.0
+    gradNormOpt: float = 0.0
+    elapsedMs: float = 0.0
+    tCGStatus: int = 4
+    outer_iterations: int = 0
+    inner_iterations: int = 0
+    accepted: bool = False
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Arg:
+    """Pointer view of a matrix argument (keeps the backing buffer alive)."""
+
+    def __init__(self, x, r, K, out=False):
+        self.torch = _is_torch(x)
+        if self.torch:
+            assert x.is_cuda and x.is_contiguous() and tuple(x.shape) == (K, r), \
+                "CUDA tensors must be contiguous with shape (K, r)"
+            self.buf = x
+            self.ptr = C.c_void_p(x.data_ptr())
+        else:
+            a = np.asarray(x, dtype=np.float64)
+            assert a.shape == (r, K), f"expected shape {(r, K)}, got {a.shape}"
+            self.buf = np.asfortranarray(a) if not out else a
+            self.ptr = self.buf.ctypes.data_as(C.c_void_p)
+
+
+def _new_out(like, r, K):
+    if _is_torch(like):
+        import torch
+        return torch.empty((K, r), dtype=torch.float64, device=like.device)
+    return np.empty((r, K), dtype=np.float64, order="F")
+
+
+class QuadraticProblem:
+    """Batch of `len(agents)` agent problems (1 = the reference's single
+    QuadraticProblem).  src/QuadraticProblem.cpp:19-34."""
+
+    def __init__(self, agents, r, d, order=ORDER_SE, device=0, _handle=None,
+                 _parent=None):
+        self.lib = _lib.load()
+        self.r, self.d, self.order, self.device = r, d, order, device
+        if _handle is not None:
+            self.h = _handle
+            self.agents = _parent.agents
+            self.A = _parent.A
+            self.K = _parent.K
+            self.koff = _parent.koff
+            return
+        if isinstance(agents, AgentData):
+            agents = [agents]
+        self.agents = agents
+        self.A = len(agents)
+        descs = (AgentDesc * self.A)()
+        keep = []
+        koff = [0]
+        for i, ag in enumerate(agents):
+            if isinstance(ag.Q, tuple):
+                rowptr, col, val = ag.Q
+            else:
+                Q = ag.Q.tocsr()
+                rowptr, col, val = Q.indptr, Q.indices, Q.data
+            rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+            col = np.ascontiguousarray(col, dtype=np.int32)
+            val = np.ascontiguousarray(val, dtype=np.float64)
+            k = (d + 1) * ag.n + ag.l + ag.b
+            assert len(rowptr) == k + 1, "Q has the wrong dimension"
+            keep += [rowptr, col, val]
+            descs[i].n, descs[i].l, descs[i].b = ag.n, ag.l, ag.b
+            descs[i].rowptr = rowptr.ctypes.data_as(_lib.c_int32_p)
+            descs[i].col = col.ctypes.data_as(_lib.c_int32_p)
+            descs[i].val = val.ctypes.data_as(_lib.c_double_p)
+            if ag.G is not None:
+                G = np.asfortranarray(np.asarray(ag.G, np.float64))
+                assert G.shape == (r, k)
+                keep.append(G)
+                descs[i].G = G.ctypes.data_as(_lib.c_double_p)
+            descs[i].precond_reg = -1.0 if ag.precond_reg is None else ag.precond_reg
+            koff.append(koff[-1] + k)
+        self.koff = koff
+        self.K = koff[-1]
+        h = C.c_void_p()
+        check(self.lib.dcora_problem_create(descs, self.A, r, d, order, device,
+                                            C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            self.lib.dcora_problem_destroy(h)
+            self.h = None
+
+    # -- dims (QuadraticProblem.h:58-94)
+    def relaxation_rank(self):
+        return self.r
+
+    def dimension(self):
+        return self.d
+
+    def problem_dimension(self):
+        return self.K
+
+    def with_rank(self, r):
+        """The same graph at another relaxation rank (the staircase re-creates
+        Graph/QuadraticProblem per rank; Q is rank independent)."""
+        h = C.c_void_p()
+        check(self.lib.dcora_problem_clone_rank(self.h, r, C.byref(h)))
+        return QuadraticProblem(None, r, self.d, self.order, self.device,
+                                _handle=h, _parent=self)
+
+    def nnz(self):
+        return self.lib.dcora_problem_nnz(self.h)
+
+    def factor_nnz(self):
+        return self.lib.dcora_problem_factor_nnz(self.h)
+
+    def launch_count(self):
+        return self.lib.dcora_problem_launch_count(self.h)
+
+    def stream(self):
+        return self.lib.dcora_problem_stream(self.h)
+
+    # -- data
+    def set_G(self, G):
+        if G is None:
+            check(self.lib.dcora_problem_set_G(self.h, None))
+        else:
+            a = _Arg(G, self.r, self.K)
+            check(self.lib.dcora_problem_set_G(self.h, a.ptr))
+
+    # -- QuadraticProblem.cpp:38-123
+    def _scalars(self, fn, X):
+        a = _Arg(X, self.r, self.K)
+        out = (C.c_double * self.A)()
+        check(fn(self.h, a.ptr, out))
+        v = np.array(out[:])
+        return float(v[0]) if self.A == 1 else v
+
+    def f(self, X):
+        return self._scalars(self.lib.dcora_problem_f, X)
+
+    def RieGradNorm(self, X):
+        return self._scalars(self.lib.dcora_problem_rgradnorm, X)
+
+    def _unary(self, fn, X):
+        a = _Arg(X, self.r, self.K)
+        out = _new_out(X, self.r, self.K)
+        o = _Arg(out, self.r, self.K, out=True)
+        check(fn(self.h, a.ptr, o.ptr))
+        return out
+
+    def _binary(self, fn, X, V, *extra):
+        a, b = _Arg(X, self.r, self.K), _Arg(V, self.r, self.K)
+        out = _new_out(X, self.r, self.K)
+        o = _Arg(out, self.r, self.K, out=True)
+        check(fn(self.h, a.ptr, b.ptr, o.ptr, *extra))
+        return out
+
+    def EucGrad(self, X):
+        return self._unary(self.lib.dcora_problem_egrad, X)
+
+    def EucHessianEta(self, V):
+        return self._unary(self.lib.dcora_problem_hessvec, V)
+
+    def RieGrad(self, X):
+        return self._unary(self.lib.dcora_problem_rgrad, X)
+
+    def PreCondition(self, X, V):
+        return self._binary(self.lib.dcora_problem_precond, X, V)
+
+    def Retract(self, X, V, retraction=RETRACT_QF):
+        return self._binary(self.lib.dcora_problem_retract, X, V, retraction)
+
+    def projectToTangentSpace(self, X, V):
+        return self._binary(self.lib.dcora_problem_project_tangent, X, V)
+
+    def project(self, M):
+        """LiftedSEManifold::project / LiftedRAManifold::project."""
+        return self._unary(self.lib.dcora_problem_project_manifold, M)
+
+    # -- QuadraticProblem.cpp:138-234
+    def escapeSaddle(self, Xopt, theta, v, gradient_tolerance,
+                     preconditioned_gradient_tolerance, isSecondOrder=False,
+                     retraction=RETRACT_QF):
+        """`self` is the rank-r problem; Xopt is (r-1) x K.  Returns (X, ok)."""
+        a = _Arg(Xopt, self.r - 1, self.K)
+        vv = np.ascontiguousarray(v, dtype=np.float64)
+        assert vv.shape == (self.K,)
+        out = np.empty((self.r, self.K), dtype=np.float64, order="F")
+        rc = check(self.lib.dcora_problem_escape_saddle(
+            self.h, a.ptr, float(theta), vv.ctypes.data_as(C.c_void_p),
+            float(gradient_tolerance), float(preconditioned_gradient_tolerance),
+            int(isSecondOrder), retraction, out.ctypes.data_as(C.c_void_p)))
+        return out, rc == 0
+
+    # -- certification (DCORA_utils.cpp:1713-1982)
+    def certify(self, X, eta, max_matvecs=20000, tol=1e-9, want_vector=True):
+        a = _Arg(X, self.r, self.K)
+        res = CertifyResult()
+        v = np.zeros(self.K) if want_vector else None
+        check(self.lib.dcora_certify(
+            self.h, a.ptr, float(eta), int(max_matvecs), float(tol), C.byref(res),
+            v.ctypes.data_as(C.c_void_p) if v is not None else None))
+        return res, v
+
+    def time_spmm(self, iters=20):
+        ms, by = C.c_double(), C.c_double()
+        check(self.lib.dcora_problem_time_spmm(self.h, iters, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+
+class QuadraticOptimizer:
+    """src/QuadraticOptimizer.cpp:20-50."""
+
+    def __init__(self, problem: QuadraticProblem, params: ROptParameters | None = None):
+        self.problem = problem
+        self.params = params or ROptParameters()
+        self.results: list[ROPTResult] = []
+
+    # setters (QuadraticOptimizer.h:52-96)
+    def setVerbose(self, v): self.params.verbose = v
+    def setAlgorithm(self, alg): self.params.method = alg
+    def setRGDStepsize(self, s): self.params.RGD_stepsize = s
+    def setRTRIterations(self, n): self.params.RTR_iterations = n
+    def setGradientNormTolerance(self, t): self.params.gradnorm_tol = t
+    def setRTRInitialRadius(self, r): self.params.RTR_initial_radius = r
+    def setRTRtCGIterations(self, n): self.params.RTR_tCG_iterations = n
+
+    def optimize(self, Y, active=None):
+        P = self.problem
+        a = _Arg(Y, P.r, P.K)
+        out = _new_out(Y, P.r, P.K)
+        o = _Arg(out, P.r, P.K, out=True)
+        res = (ROptResult * P.A)()
+        prm = self.params.to_c()
+        act = None
+        if active is not None:
+            act_arr = np.ascontiguousarray(active, dtype=np.uint8)
+            assert act_arr.shape == (P.A,)
+            act = act_arr.ctypes.data_as(_lib.c_uint8_p)
+        check(P.lib.dcora_rtr_solve(P.h, a.ptr, o.ptr, C.byref(prm), act, res))
+        self.results = [ROPTResult(bool(x.success), x.fInit, x.gradNormInit, x.fOpt,
+                                   x.gradNormOpt, x.elapsedMs, x.tCGStatus,
+                                   x.outer_iterations, x.inner_iterations,
+                                   bool(x.accepted)) for x in res]
+        return out
+
+    def getOptResult(self):
+        return self.results[0] if len(self.results) == 1 else self.results

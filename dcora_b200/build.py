@@ -1,0 +1,62 @@
+"""In-tree build of libdcora_b200.so for sm_100a (nvcc, no torch dependency)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libdcora_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["layout.cpp", "chol.cpp", "selfcheck.cpp", "kernels.cu", "sptrsv.cu", "problem.cu",
+           "solver.cu", "certify.cu", "rbcd.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+         "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr", "-diag-suppress", "128"]
+
+
+def _deps_hash(src):
+    h = hashlib.sha1()
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cuh", ".h")) or name == src:
+            with open(os.path.join(CSRC, name), "rb") as fh:
+                h.update(fh.read())
+    with open(os.path.join(HERE, "..", "include", "dcora_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src):
+    obj = os.path.join(BUILD, src + ".o")
+    stamp = obj + ".sha1"
+    want = _deps_hash(src)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+        return obj, False
+    cmd = [NVCC, *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+    subprocess.run(cmd, check=True)
+    with open(stamp, "w") as fh:
+        fh.write(want)
+    return obj, True
+
+
+def build(verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(_compile, srcs))
+    objs = [o for o, _ in results]
+    if any(ch for _, ch in results) or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp",
+               "-lgomp", "-lcudart"]
+        subprocess.run(cmd, check=True)
+    if verbose:
+        print("built", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(verbose=True)

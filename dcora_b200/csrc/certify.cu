@@ -1,0 +1,485 @@
+// K6/K7: dual certificate S = Q - Lambda applied implicitly, and lambda_min(S)
+// by a device thick-restart Lanczos over the K1 SpMV (r = 1).
+//
+// Replaces constructDualCertificateMatrix{PGO,RASLAM} (DCORA_utils.cpp:1898-1982),
+// fastVerification / isSparseSymmetricMatrixPSD (:1713-1747, CHOLMOD) and
+// computeMinimumEigenPair (:1751-1896, Spectra v1.0.1).  Spectra's implicitly
+// restarted Lanczos and the thick-restart Lanczos used here span the same
+// Krylov spaces; S is never materialised.  Also hosts escapeSaddle
+// (QuadraticProblem.cpp:138-234).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "solver.cuh"
+
+namespace dcora {
+
+namespace {
+
+// out = qv - Lambda * v  (Lambda blocks live in a rank-R shaped buffer, see
+// launch_sym_ytg: d*d per pose block at pb = col0*R, one scalar per sphere)
+template <int DH>
+__global__ void __launch_bounds__(128)
+lambda_apply_kernel(const Chunk *__restrict__ chunks, int R,
+                    const double *__restrict__ Lam, const double *__restrict__ v,
+                    const double *__restrict__ qv, double *__restrict__ out) {
+  constexpr int D = DH - 1;
+  const Chunk ch = chunks[blockIdx.x];
+  if (ch.kind == KIND_POSE) {
+    for (int t = threadIdx.x; t < ch.ncols; t += 128) {
+      const int pi = t / DH, a = t - pi * DH;
+      const int col = ch.col0 + t;
+      double s = qv[col];
+      if (a < D) {
+        const size_t pb = (size_t)(ch.col0 + pi * DH) * R;
+#pragma unroll
+        for (int b = 0; b < D; ++b) s -= Lam[pb + a * D + b] * v[ch.col0 + pi * DH + b];
+      }
+      out[col] = s;
+    }
+  } else if (ch.kind == KIND_SPHERE) {
+    for (int t = threadIdx.x; t < ch.ncols; t += 128) {
+      const int col = ch.col0 + t;
+      out[col] = qv[col] - Lam[(size_t)col * R] * v[col];
+    }
+  } else {
+    for (int t = threadIdx.x; t < ch.ncols; t += 128) out[ch.col0 + t] = qv[ch.col0 + t];
+  }
+}
+
+constexpr int LZ_BLOCK = 256;
+constexpr int LZ_ROWS = 2048;   // rows per CTA in the tall-skinny kernels
+constexpr int LZ_MAXM = 64;
+
+// partial[blk][c] = sum_{i in blk} V[c][i] * w[i],  c < j
+__global__ void __launch_bounds__(LZ_BLOCK)
+basis_dots_kernel(const double *__restrict__ V, int64_t ld, int j,
+                  const double *__restrict__ w, int64_t K, double *__restrict__ partial) {
+  __shared__ double sm[LZ_BLOCK / 32];
+  const int64_t i0 = (int64_t)blockIdx.x * LZ_ROWS;
+  const int64_t i1 = min(K, i0 + LZ_ROWS);
+  for (int c = 0; c < j; ++c) {
+    const double *vc = V + (size_t)c * ld;
+    double acc = 0.0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += LZ_BLOCK) acc = fma(vc[i], w[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < LZ_BLOCK / 32; ++q) t += sm[q];
+      partial[(size_t)blockIdx.x * LZ_MAXM + c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// h[c] = sum_blk partial[blk][c]  (fixed order)
+__global__ void __launch_bounds__(LZ_BLOCK)
+basis_dots_reduce_kernel(const double *__restrict__ partial, int nblk, int j,
+                         double *__restrict__ h) {
+  __shared__ double sm[LZ_BLOCK / 32];
+  const int c = blockIdx.x;
+  if (c >= j) return;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += LZ_BLOCK) acc += partial[(size_t)b * LZ_MAXM + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < LZ_BLOCK / 32; ++q) t += sm[q];
+    h[c] = t;
+  }
+}
+
+// w[i] -= sum_c V[c][i] h[c]
+__global__ void __launch_bounds__(LZ_BLOCK)
+basis_axpy_kernel(const double *__restrict__ V, int64_t ld, int j,
+                  const double *__restrict__ h, double *__restrict__ w, int64_t K) {
+  __shared__ double sh[LZ_MAXM];
+  if (threadIdx.x < j) sh[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * LZ_BLOCK + threadIdx.x;
+  if (i >= K) return;
+  double acc = w[i];
+  for (int c = 0; c < j; ++c) acc = fma(-sh[c], V[(size_t)c * ld + i], acc);
+  w[i] = acc;
+}
+
+// out[c][i] = sum_q V[q][i] * Y[q*ldy + c],  c < kk  (Ritz vectors)
+__global__ void __launch_bounds__(LZ_BLOCK)
+basis_rotate_kernel(const double *__restrict__ V, int64_t ld, int m, int kk,
+                    const double *__restrict__ Y, double *__restrict__ out, int64_t K) {
+  extern __shared__ double sy[];  // m * kk
+  for (int t = threadIdx.x; t < m * kk; t += LZ_BLOCK) sy[t] = Y[t];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * LZ_BLOCK + threadIdx.x;
+  if (i >= K) return;
+  for (int c0 = 0; c0 < kk; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    for (int q = 0; q < m; ++q) {
+      const double v = V[(size_t)q * ld + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < kk) acc[u] = fma(v, sy[q * kk + c0 + u], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (c0 + u < kk) out[(size_t)(c0 + u) * ld + i] = acc[u];
+  }
+}
+
+__global__ void __launch_bounds__(LZ_BLOCK)
+scale_copy_kernel(const double *__restrict__ x, double s, double *__restrict__ y, int64_t K) {
+  const int64_t i = (int64_t)blockIdx.x * LZ_BLOCK + threadIdx.x;
+  if (i < K) y[i] = s * x[i];
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (host, tiny)
+void jacobi_eig(int n, std::vector<double> &Amat, std::vector<double> &evec,
+                std::vector<double> &eval) {
+  evec.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) evec[(size_t)i * n + i] = 1.0;
+  auto Aat = [&](int i, int j) -> double & { return Amat[(size_t)i * n + j]; };
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? dg : off) += Aat(i, j) * Aat(i, j);
+    if (off <= 1e-32 * (dg + 1e-300)) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = Aat(p, q);
+        if (std::fabs(apq) < 1e-300) continue;
+        const double tau = (Aat(q, q) - Aat(p, p)) / (2.0 * apq);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = Aat(k, p), akq = Aat(k, q);
+          Aat(k, p) = c * akp - s * akq;
+          Aat(k, q) = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = Aat(p, k), aqk = Aat(q, k);
+          Aat(p, k) = c * apk - s * aqk;
+          Aat(q, k) = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = evec[(size_t)k * n + p], vkq = evec[(size_t)k * n + q];
+          evec[(size_t)k * n + p] = c * vkp - s * vkq;
+          evec[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  eval.resize(n);
+  for (int i = 0; i < n; ++i) eval[i] = Aat(i, i);
+}
+
+}  // namespace
+
+// sub-handle of rank 1 sharing matrices and stream with `p`
+static int make_rank1(dcora_problem *p, dcora_problem **q) {
+  dcora_problem *s = nullptr;
+  DCORA_TRY(dcora_problem_clone_rank(p, 1, &s));
+  cudaStreamDestroy(s->stream);
+  s->stream = p->stream;
+  s->owns_stream = false;
+  *q = s;
+  return DCORA_OK;
+}
+
+static int apply_S(dcora_problem *p, dcora_problem *q1, const double *Lam,
+                   const double *v, double *tmp, double *out) {
+  DeviceMatrices &M = *p->M;
+  DCORA_TRY(launch_spmm(q1, v, nullptr, tmp, -1));
+  if (M.d == 3)
+    lambda_apply_kernel<4><<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->r, Lam, v, tmp, out);
+  else
+    lambda_apply_kernel<3><<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->r, Lam, v, tmp, out);
+  DCORA_LAUNCH_CHECK(p);
+  return DCORA_OK;
+}
+
+}  // namespace dcora
+
+using namespace dcora;
+
+extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
+                             int32_t max_matvecs, double tol,
+                             dcora_certify_result *res, double *v_out) {
+  if (!p || !X || !res) return DCORA_ERR_ARG;
+  if (p->M->A != 1) {
+    set_error("dcora_certify needs a centralised problem (num_agents == 1)");
+    return DCORA_ERR_ARG;
+  }
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  DeviceMatrices &M = *p->M;
+  const int64_t K = M.K;
+  double *x = p->vec(WS_IO0), *xq = p->vec(WS_IO1), *Lam = p->vec(WS_S);
+  if (!x || !xq || !Lam) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  // Lambda = sym-block-diag(X^T (X Q)) -- G is ignored exactly as the
+  // reference does (valid for the centralised problem only)
+  DCORA_TRY(launch_spmm(p, x, nullptr, xq, -1));
+  DCORA_TRY(launch_sym_ytg(p, x, xq, Lam, -1));
+
+  dcora_problem *q1 = nullptr;
+  DCORA_TRY(make_rank1(p, &q1));
+  struct Guard { dcora_problem *q; ~Guard() { delete q; } } guard{q1};
+
+  const int m = (int)std::min<int64_t>(48, K);        // Krylov dimension
+  const int keep = std::max(1, std::min(m / 2, 16));  // Ritz vectors kept
+  double *basis[2] = {nullptr, nullptr};
+  double *w = nullptr, *tmp = nullptr, *d_h = nullptr, *d_part = nullptr, *d_Y = nullptr;
+  const int nblk = (int)((K + LZ_ROWS - 1) / LZ_ROWS);
+  const int gridK = (int)((K + LZ_BLOCK - 1) / LZ_BLOCK);
+  auto cleanup = [&]() {
+    cudaFree(basis[0]); cudaFree(basis[1]); cudaFree(w); cudaFree(tmp);
+    cudaFree(d_h); cudaFree(d_part); cudaFree(d_Y);
+  };
+#define CERT_CUDA(call)                                    \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+      cleanup();                                           \
+      return DCORA_ERR_CUDA;                               \
+    }                                                      \
+  } while (0)
+  CERT_CUDA(cudaMalloc(&basis[0], sizeof(double) * (size_t)(m + 1) * K));
+  CERT_CUDA(cudaMalloc(&basis[1], sizeof(double) * (size_t)(m + 1) * K));
+  CERT_CUDA(cudaMalloc(&w, sizeof(double) * K));
+  CERT_CUDA(cudaMalloc(&tmp, sizeof(double) * K));
+  CERT_CUDA(cudaMalloc(&d_h, sizeof(double) * LZ_MAXM));
+  CERT_CUDA(cudaMalloc(&d_part, sizeof(double) * (size_t)nblk * LZ_MAXM));
+  CERT_CUDA(cudaMalloc(&d_Y, sizeof(double) * LZ_MAXM * LZ_MAXM));
+
+  // deterministic start vector (the reference perturbs S.row(0) randomly,
+  // DCORA_utils.cpp:1862-1866; any vector with a component along the minimum
+  // eigenvector will do)
+  {
+    std::vector<double> v0(K);
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    double nrm = 0.0;
+    for (int64_t i = 0; i < K; ++i) {
+      st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+      v0[i] = (double)(st >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+      nrm += v0[i] * v0[i];
+    }
+    nrm = 1.0 / std::sqrt(nrm);
+    for (int64_t i = 0; i < K; ++i) v0[i] *= nrm;
+    CERT_CUDA(cudaMemcpyAsync(basis[0], v0.data(), sizeof(double) * K, cudaMemcpyHostToDevice,
+                              p->stream));
+    CERT_CUDA(cudaStreamSynchronize(p->stream));
+  }
+
+  std::vector<double> T((size_t)m * m, 0.0), evec, eval, h(LZ_MAXM), Yk;
+  int cur = 0, k = 0, matvecs = 0, restarts = 0, converged = 0;
+  double lam = 0.0, resid = 0.0, scale = 0.0;
+  std::vector<double> best_y(m, 0.0);
+  int rc = DCORA_OK;
+  while (true) {
+    double *V = basis[cur];
+    double beta_last = 0.0;
+    for (int j = k; j < m; ++j) {
+      rc = apply_S(p, q1, Lam, V + (size_t)j * K, tmp, w);
+      if (rc < 0) { cleanup(); return rc; }
+      ++matvecs;
+      // two passes of classical Gram-Schmidt against V[0..j]; the first pass
+      // yields the projected matrix column (alpha_j and, after a restart, the
+      // coupling row)
+      for (int pass = 0; pass < 2; ++pass) {
+        basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(V, K, j + 1, w, K, d_part);
+        basis_dots_reduce_kernel<<<j + 1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, j + 1, d_h);
+        basis_axpy_kernel<<<gridK, LZ_BLOCK, 0, p->stream>>>(V, K, j + 1, d_h, w, K);
+        p->launches += 3;
+        if (pass == 0) {
+          CERT_CUDA(cudaMemcpyAsync(h.data(), d_h, sizeof(double) * (j + 1),
+                                    cudaMemcpyDeviceToHost, p->stream));
+          CERT_CUDA(cudaStreamSynchronize(p->stream));
+          T[(size_t)j * m + j] = h[j];
+        }
+      }
+      // beta_j = ||w||
+      basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(w, K, 1, w, K, d_part);
+      basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
+      p->launches += 2;
+      double bb = 0.0;
+      CERT_CUDA(cudaMemcpyAsync(&bb, d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      CERT_CUDA(cudaStreamSynchronize(p->stream));
+      const double beta = std::sqrt(std::max(0.0, bb));
+      beta_last = beta;
+      if (j + 1 < m) { T[(size_t)(j + 1) * m + j] = beta; T[(size_t)j * m + j + 1] = beta; }
+      const double inv = beta > 1e-300 ? 1.0 / beta : 0.0;
+      scale_copy_kernel<<<gridK, LZ_BLOCK, 0, p->stream>>>(w, inv, V + (size_t)(j + 1) * K, K);
+      p->launches += 1;
+    }
+    // Ritz pairs of the projected matrix
+    std::vector<double> Tc(T);
+    jacobi_eig(m, Tc, evec, eval);
+    std::vector<int> idx(m);
+    for (int i = 0; i < m; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return eval[a] < eval[b]; });
+    scale = 0.0;
+    for (int i = 0; i < m; ++i) scale = std::max(scale, std::fabs(eval[i]));
+    lam = eval[idx[0]];
+    resid = std::fabs(beta_last * evec[(size_t)(m - 1) * m + idx[0]]);
+    for (int q = 0; q < m; ++q) best_y[q] = evec[(size_t)q * m + idx[0]];
+    ++restarts;
+    converged = resid <= tol * std::max(scale, 1e-300);
+    // early verdict: lambda_min <= lam always (Ritz values bound from above),
+    // so a Ritz value below -eta already decides "not PSD" once its residual
+    // is small relative to the margin
+    if (converged || matvecs >= max_matvecs || beta_last <= 1e-300) break;
+    // thick restart: keep the `keep` smallest Ritz vectors
+    const int kk = std::min(keep, m - 1);
+    Yk.assign((size_t)m * kk, 0.0);
+    for (int q = 0; q < m; ++q)
+      for (int c = 0; c < kk; ++c) Yk[(size_t)q * kk + c] = evec[(size_t)q * m + idx[c]];
+    CERT_CUDA(cudaMemcpyAsync(d_Y, Yk.data(), sizeof(double) * m * kk, cudaMemcpyHostToDevice,
+                              p->stream));
+    double *Vn = basis[1 - cur];
+    basis_rotate_kernel<<<gridK, LZ_BLOCK, sizeof(double) * m * kk, p->stream>>>(V, K, m, kk,
+                                                                                 d_Y, Vn, K);
+    CERT_CUDA(cudaMemcpyAsync(Vn + (size_t)kk * K, V + (size_t)m * K, sizeof(double) * K,
+                              cudaMemcpyDeviceToDevice, p->stream));
+    p->launches += 1;
+    std::fill(T.begin(), T.end(), 0.0);
+    for (int c = 0; c < kk; ++c) {
+      T[(size_t)c * m + c] = eval[idx[c]];
+      const double s = beta_last * evec[(size_t)(m - 1) * m + idx[c]];
+      T[(size_t)kk * m + c] = s;
+      T[(size_t)c * m + kk] = s;
+    }
+    CERT_CUDA(cudaStreamSynchronize(p->stream));
+    cur = 1 - cur;
+    k = kk;
+  }
+  // minimum Ritz vector v = V y
+  {
+    double *V = basis[cur];
+    CERT_CUDA(cudaMemcpyAsync(d_Y, best_y.data(), sizeof(double) * m, cudaMemcpyHostToDevice,
+                              p->stream));
+    basis_rotate_kernel<<<gridK, LZ_BLOCK, sizeof(double) * m, p->stream>>>(V, K, m, 1, d_Y, w, K);
+    p->launches += 1;
+    // theta = v^T S v (fastVerification :1727)
+    rc = apply_S(p, q1, Lam, w, tmp, basis[1 - cur]);
+    if (rc < 0) { cleanup(); return rc; }
+    basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(basis[1 - cur], K, 1, w, K, d_part);
+    basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
+    basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(w, K, 1, w, K, d_part + (size_t)nblk * 0);
+    p->launches += 2;
+    double vSv = 0.0;
+    CERT_CUDA(cudaMemcpyAsync(&vSv, d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CERT_CUDA(cudaStreamSynchronize(p->stream));
+    basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
+    double vv = 1.0;
+    CERT_CUDA(cudaMemcpyAsync(&vv, d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CERT_CUDA(cudaStreamSynchronize(p->stream));
+    res->theta = vSv / vv;
+    if (v_out) {
+      scale_copy_kernel<<<gridK, LZ_BLOCK, 0, p->stream>>>(w, 1.0 / std::sqrt(vv), tmp, K);
+      rc = export_matrix(q1, tmp, v_out, 1);
+      if (rc < 0) { cleanup(); return rc; }
+      CERT_CUDA(cudaStreamSynchronize(p->stream));
+    }
+  }
+  res->lambda_min = lam;
+  res->residual = resid;
+  res->converged = converged;
+  res->matvecs = matvecs;
+  res->restarts = restarts;
+  res->is_psd = (lam + eta > 0.0) ? 1 : 0;
+  cleanup();
+#undef CERT_CUDA
+  return DCORA_OK;
+}
+
+extern "C" int dcora_problem_escape_saddle(dcora_problem *p, const double *Xopt,
+                                           double theta, const double *v,
+                                           double gradient_tolerance,
+                                           double preconditioned_gradient_tolerance,
+                                           int32_t is_second_order, int32_t retraction,
+                                           double *Xout) {
+  if (!p || !Xopt || !v || !Xout) return DCORA_ERR_ARG;
+  if (p->M->A != 1 || p->r < 2) {
+    set_error("escape_saddle needs a single-agent problem of rank >= 2");
+    return DCORA_ERR_ARG;
+  }
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  const int r = p->r;
+  const int64_t K = p->M->K;
+  // Host assembly of X_plus = [Xopt; 0] and X_dot = [0; v^T] in the reference
+  // layout (QuadraticProblem.cpp:148-154); everything else runs on the device.
+  std::vector<double> hx((size_t)r * K, 0.0), hd((size_t)r * K, 0.0), hin;
+  const double *src = Xopt;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, Xopt) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+    hin.resize((size_t)(r - 1) * K);
+    DCORA_CUDA(cudaMemcpy(hin.data(), Xopt, sizeof(double) * hin.size(), cudaMemcpyDeviceToHost));
+    src = hin.data();
+  } else {
+    cudaGetLastError();
+  }
+  for (int64_t c = 0; c < K; ++c) {
+    for (int q = 0; q < r - 1; ++q) hx[(size_t)c * r + q] = src[(size_t)c * (r - 1) + q];
+    hd[(size_t)c * r + (r - 1)] = v[c];
+  }
+  double *xp = p->vec(WS_X1), *xd = p->vec(WS_ETA), *step = p->vec(WS_DELTA);
+  double *xt = p->vec(WS_X2), *t0 = p->vec(WS_T0), *eg = p->vec(WS_EG), *g = p->vec(WS_GF);
+  double *pg = p->vec(WS_Z);
+  if (!xp || !xd || !step || !xt || !t0 || !eg || !g || !pg) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, hx.data(), xp, r));
+  DCORA_TRY(import_matrix(p, hd.data(), xd, r));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+
+  const double alpha_min = 1e-6;
+  double alpha = is_second_order
+                     ? std::max(16 * alpha_min, 100 * gradient_tolerance / std::fabs(theta))
+                     : 1.0;
+  DCORA_TRY(eval_f(p, xp, t0, S_TMP0, -1));
+  DCORA_TRY(read_scalars(p));
+  const double FX = p->h_scal[S_TMP0];
+  std::vector<double> alphas, fvals;
+  auto trial = [&](double a, double *f, double *gn, double *pgn) -> int {
+    DCORA_TRY(launch_axpby(p, step, -1, a, xd, -1, 0.0, nullptr, -1));
+    DCORA_TRY(launch_retract(p, xp, step, xt, retraction, -1));
+    DCORA_TRY(eval_f(p, xt, t0, S_TMP0, -1));
+    if (gn) {
+      DCORA_TRY(launch_spmm(p, xt, p->has_G ? p->G : nullptr, eg, -1));
+      DCORA_TRY(launch_project_tangent(p, xt, eg, g, -1));
+      DCORA_TRY(launch_precond(p, xt, g, pg, -1));
+      const double *xs[2] = {g, pg};
+      DCORA_TRY(launch_dots(p, 2, xs, xs, -1));
+      const int dst[2] = {S_TMP1, S_TMP2};
+      DCORA_TRY(launch_reduce_scalars(p, 2, dst));
+    }
+    DCORA_TRY(read_scalars(p));
+    *f = p->h_scal[S_TMP0];
+    if (gn) { *gn = std::sqrt(p->h_scal[S_TMP1]); *pgn = std::sqrt(p->h_scal[S_TMP2]); }
+    return DCORA_OK;
+  };
+  while (alpha >= alpha_min) {
+    double ft, gn, pgn;
+    DCORA_TRY(trial(alpha, &ft, &gn, &pgn));
+    alphas.push_back(alpha);
+    fvals.push_back(ft);
+    if (ft < FX && gn > gradient_tolerance && pgn > preconditioned_gradient_tolerance)
+      return export_matrix(p, xt, Xout, r);
+    alpha /= 2;
+  }
+  const size_t imin = std::min_element(fvals.begin(), fvals.end()) - fvals.begin();
+  if (!fvals.empty() && fvals[imin] < FX) {
+    double ft;
+    DCORA_TRY(trial(alphas[imin], &ft, nullptr, nullptr));
+    return export_matrix(p, xt, Xout, r);
+  }
+  return DCORA_SOFT_FAIL;
+}

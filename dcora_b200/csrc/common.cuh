@@ -1,0 +1,151 @@
+// dcora_b200 internal definitions shared by the .cu / .cpp translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dcora_b200.h"
+
+namespace dcora {
+
+constexpr int MAX_RANK = 16;      // templated ranks 1..MAX_RANK
+constexpr int POSE_CHUNK = 64;    // poses per chunk (pose region)
+constexpr int EXTRA_CHUNK = 512;  // columns per chunk (sphere / landmark region)
+constexpr int NUM_SMS = 148;      // B200
+
+void set_error(const std::string &msg);
+
+#define DCORA_CUDA(call)                                                        \
+  do {                                                                          \
+    cudaError_t err__ = (call);                                                 \
+    if (err__ != cudaSuccess) {                                                 \
+      ::dcora::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + \
+                         " at " + __FILE__ + ":" + std::to_string(__LINE__));   \
+      return DCORA_ERR_CUDA;                                                    \
+    }                                                                           \
+  } while (0)
+
+#define DCORA_TRY(call)            \
+  do {                             \
+    int rc__ = (call);             \
+    if (rc__ < 0) return rc__;     \
+  } while (0)
+
+// A chunk is a run of internal columns that belongs to one agent and one
+// manifold factor kind; every vector kernel is launched one CTA per chunk so
+// that per-agent reductions are deterministic and per-agent masks are cheap.
+enum ChunkKind : int { KIND_POSE = 0, KIND_SPHERE = 1, KIND_EUCLID = 2 };
+struct Chunk {
+  int col0;   // first internal column
+  int ncols;  // number of columns (pose chunks: multiple of d+1)
+  int kind;
+  int agent;
+};
+
+// Host-side result of converting the agents' CSR matrices (reference
+// ordering) to the internal device layout.  See layout.cpp.
+struct HostLayout {
+  int r = 0, d = 0, order = 0, A = 0;
+  int64_t K = 0;           // total columns
+  int64_t nnz_in = 0;      // nnz(Q) as given
+  std::vector<int64_t> coff;  // A+1 column offsets (internal == reference)
+  std::vector<int> n, l, b;   // per agent
+  std::vector<int> poff;      // A+1 pose offsets
+  bool identity_perm = true;
+  std::vector<int> perm;      // internal col -> reference col (global), size K
+  // BSR of Q^T over pose blocks (row = output pose block)
+  int np = 0;
+  std::vector<int> browptr, bcol;  // bcol = internal column start of block col
+  std::vector<double> bval;        // [a][b] row-major, a = output col in block
+  std::vector<int> prowcol;        // np: internal col start of pose block row
+  // scalar remainder (entries touching a sphere / landmark row or column)
+  std::vector<int> rem_row, rem_rowptr, rem_col;
+  std::vector<uint8_t> rem_assign;  // 1: Y[row] = sum, 0: Y[row] += sum
+  std::vector<double> rem_val;
+  std::vector<Chunk> chunks;
+  std::vector<int> agent_chunk0;  // A+1
+};
+
+int build_layout(const dcora_agent_desc *agents, int A, int r, int d, int order,
+                 HostLayout *out);
+
+// Host sparse Cholesky factor of one agent (chol.cpp), internal ordering.
+struct HostFactor {
+  int k = 0;
+  std::vector<int> perm;            // new -> old (internal col within agent)
+  std::vector<int> Lp, Li;          // CSC of L (k+1, nnz), rows sorted
+  std::vector<double> Lx;
+};
+// A given as full symmetric CSR (internal ordering, agent-local); `dh` and
+// `npose` describe the supervariable structure used by the ordering.
+int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
+                    const std::vector<double> &Ax, int dh, int npose,
+                    HostFactor *out);
+
+// Device-side factor for the whole batch (sptrsv.cu).
+struct DeviceFactor {
+  bool present = false;
+  int64_t nnzL = 0;
+  int A = 0;
+  // forward: rows of L (CSR, strictly-lower part + inverse diagonal)
+  int *rowptr = nullptr, *colidx = nullptr;
+  double *val = nullptr;
+  // backward: rows of L^T == columns of L (CSC)
+  int *t_rowptr = nullptr, *t_colidx = nullptr;
+  double *t_val = nullptr;
+  double *inv_diag = nullptr;  // K
+  int *perm = nullptr;         // K: factor row (global) -> internal column
+  // level schedules, per agent: rows sorted by level
+  int *fwd_rows = nullptr, *bwd_rows = nullptr;        // K each (global row ids)
+  int *fwd_lvlptr = nullptr, *bwd_lvlptr = nullptr;    // concatenated per agent
+  int *fwd_lvl0 = nullptr, *bwd_lvl0 = nullptr;        // A+1 offsets into lvlptr
+  void release();
+};
+
+struct DeviceMatrices {
+  int device = 0;
+  int d = 0, order = 0, A = 0, np = 0;
+  int64_t K = 0, nnz_in = 0, nnzb = 0, nrem_rows = 0, nrem = 0;
+  int nchunks = 0;
+  std::vector<int64_t> coff;
+  std::vector<int> n, l, b, poff, agent_chunk0_h;
+  bool identity_perm = true;
+  int *perm = nullptr;
+  int *browptr = nullptr, *bcol = nullptr, *prowcol = nullptr;
+  int *pose_agent = nullptr;  // np: agent of each pose block row
+  int *rem_agent = nullptr;   // nrem_rows: agent of each remainder row
+  double *bval = nullptr;
+  int *rem_row = nullptr, *rem_rowptr = nullptr, *rem_col = nullptr;
+  uint8_t *rem_assign = nullptr;
+  double *rem_val = nullptr;
+  Chunk *chunks = nullptr;
+  int *agent_chunk0 = nullptr;
+  DeviceFactor F;
+  ~DeviceMatrices();
+};
+
+}  // namespace dcora
+
+// The opaque handle.
+struct dcora_problem {
+  int r = 0;
+  std::shared_ptr<dcora::DeviceMatrices> M;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  int64_t launches = 0;
+  size_t vec_len = 0;              // r*K doubles
+  double *G = nullptr;             // internal layout (always allocated, zero if none)
+  bool has_G = false;
+  std::vector<double *> ws;        // workspace vectors (internal layout)
+  double *stage = nullptr;         // staging vector (reference layout)
+  double *partials = nullptr;      // nchunks * NPART doubles
+  double *scal = nullptr;          // per-agent scalar block (device)
+  double *h_scal = nullptr;        // pinned mirror
+  int *flags = nullptr;            // per-agent int flags (device)
+  int *h_flags = nullptr;          // pinned mirror
+  double *vec(int i);              // lazily allocated workspace vector i
+  ~dcora_problem();
+};

@@ -1,0 +1,228 @@
+// Host-side conversion of the agents' data matrices (CSR, reference column
+// ordering) to the device layout used by the sm_100a kernels.
+//
+// Internal column order of agent a (columns [coff_a, coff_a + k_a)):
+//     [ Y_1 p_1 | Y_2 p_2 | ... | Y_n p_n | r_1 .. r_l | L_1 .. L_b ]
+// i.e. pose blocks of (d+1) contiguous columns, then unit spheres, then
+// landmarks.  For DCORA_ORDER_SE this is the reference ordering itself
+// (include/DCORA/manifold/LiftedVariable.h:27-30); for DCORA_ORDER_RA
+// ([Y..|r..|p..|L..], LiftedVariable.h:148-152) it is a permutation that is
+// applied on device when matrices cross the C-ABI.
+//
+// Q is split into
+//   * BSR over pose blocks, dense (d+1)x(d+1) blocks, one 128-byte line per
+//     3-D block (the connection-Laplacian part, Graph.cpp:579-683 / Q11,Q13,
+//     pose part of Q33, Graph.cpp:1137-1141);
+//   * a scalar CSR remainder holding every entry that touches a unit-sphere
+//     or landmark row/column (Q22, Q23, landmark part of Q33).
+// Both store Q^T (output-column major) so that Y = X*Q is reproduced with the
+// reference's own pairing of operands even if Q is only symmetric to rounding.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dcora {
+
+static inline int ref_to_internal(int c, int d, int n, int l, int order) {
+  if (order == DCORA_ORDER_SE) return c;
+  const int dn = d * n;
+  if (c < dn) return (c / d) * (d + 1) + (c % d);         // rotation column
+  if (c < dn + l) return (d + 1) * n + (c - dn);          // unit sphere
+  if (c < dn + l + n) return (c - dn - l) * (d + 1) + d;  // translation
+  return (d + 1) * n + l + (c - dn - l - n);              // landmark
+}
+
+namespace {
+struct AgentLayout {
+  std::vector<int> m;                // reference col -> internal col (local)
+  std::vector<int> browptr, bcol;    // local block cols (pose index j)
+  std::vector<double> bval;
+  std::vector<int> rem_row, rem_rowptr, rem_col;  // local internal indices
+  std::vector<uint8_t> rem_assign;
+  std::vector<double> rem_val;
+  int rc = DCORA_OK;
+};
+
+void convert_agent(const dcora_agent_desc &g, int d, int order, AgentLayout *out) {
+  AgentLayout &L = *out;
+  const int dh = d + 1;
+  const int k = dh * g.n + g.l + g.b;
+  const int npc = dh * g.n;
+  L.m.resize(k);
+  for (int c = 0; c < k; ++c) L.m[c] = ref_to_internal(c, d, g.n, g.l, order);
+  // pass A: block-column sets per output block row; remainder counts
+  std::vector<std::vector<int>> cols(g.n);
+  std::vector<int> rem_count(k, 0);
+  for (int R = 0; R < k; ++R) {
+    const int ri = L.m[R];
+    for (int p = g.rowptr[R]; p < g.rowptr[R + 1]; ++p) {
+      const int C = g.col[p];
+      if (C < 0 || C >= k) { L.rc = DCORA_ERR_ARG; return; }
+      const int ci = L.m[C];
+      if (ri < npc && ci < npc) {
+        std::vector<int> &v = cols[ci / dh];
+        const int j = ri / dh;
+        if (std::find(v.begin(), v.end(), j) == v.end()) v.push_back(j);
+      } else {
+        rem_count[ci]++;
+      }
+    }
+  }
+  L.browptr.assign(g.n + 1, 0);
+  for (int i = 0; i < g.n; ++i) {
+    std::sort(cols[i].begin(), cols[i].end());
+    L.browptr[i + 1] = L.browptr[i] + (int)cols[i].size();
+  }
+  L.bcol.resize(L.browptr[g.n]);
+  for (int i = 0; i < g.n; ++i)
+    std::copy(cols[i].begin(), cols[i].end(), L.bcol.begin() + L.browptr[i]);
+  std::vector<std::vector<int>>().swap(cols);
+  L.bval.assign((size_t)L.bcol.size() * dh * dh, 0.0);
+  // remainder rows: every sphere/landmark row (assign) + pose rows with entries
+  std::vector<int> slot(k, -1);
+  L.rem_rowptr.assign(1, 0);
+  for (int ci = 0; ci < k; ++ci) {
+    const bool extra = ci >= npc;
+    if (extra || rem_count[ci] > 0) {
+      slot[ci] = (int)L.rem_row.size();
+      L.rem_row.push_back(ci);
+      L.rem_assign.push_back(extra ? 1 : 0);
+      L.rem_rowptr.push_back(L.rem_rowptr.back() + rem_count[ci]);
+    }
+  }
+  L.rem_col.assign(L.rem_rowptr.back(), 0);
+  L.rem_val.assign(L.rem_rowptr.back(), 0.0);
+  std::vector<int> fill(L.rem_rowptr.begin(), L.rem_rowptr.end() - 1);
+  // pass B: values.  Entry (R, C, v) of Q contributes X[:,R]*v to Y[:,C].
+  for (int R = 0; R < k; ++R) {
+    const int ri = L.m[R];
+    for (int p = g.rowptr[R]; p < g.rowptr[R + 1]; ++p) {
+      const int ci = L.m[g.col[p]];
+      const double v = g.val[p];
+      if (ri < npc && ci < npc) {
+        const int i = ci / dh, aa = ci % dh, j = ri / dh, bb = ri % dh;
+        const int *b0 = L.bcol.data() + L.browptr[i];
+        const int *b1 = L.bcol.data() + L.browptr[i + 1];
+        const int64_t q = std::lower_bound(b0, b1, j) - L.bcol.data();
+        L.bval[(size_t)q * dh * dh + aa * dh + bb] += v;
+      } else {
+        const int w = fill[slot[ci]]++;
+        L.rem_col[w] = ri;
+        L.rem_val[w] = v;
+      }
+    }
+  }
+}
+}  // namespace
+
+int build_layout(const dcora_agent_desc *agents, int A, int r, int d, int order,
+                 HostLayout *out) {
+  if (A <= 0 || !agents || (d != 2 && d != 3) || r < 1 || r > MAX_RANK) {
+    set_error("build_layout: bad arguments (need d in {2,3}, 1<=r<=16)");
+    return DCORA_ERR_ARG;
+  }
+  HostLayout &H = *out;
+  H.r = r; H.d = d; H.order = order; H.A = A;
+  const int dh = d + 1;
+  H.coff.assign(A + 1, 0);
+  H.poff.assign(A + 1, 0);
+  H.n.resize(A); H.l.resize(A); H.b.resize(A);
+  H.nnz_in = 0;
+  for (int a = 0; a < A; ++a) {
+    const dcora_agent_desc &g = agents[a];
+    if (g.n < 0 || g.l < 0 || g.b < 0 || !g.rowptr || (!g.col && g.rowptr[0] != 0)) {
+      set_error("build_layout: bad agent descriptor");
+      return DCORA_ERR_ARG;
+    }
+    if (order == DCORA_ORDER_SE && (g.l || g.b)) {
+      set_error("build_layout: SE ordering cannot carry unit spheres / landmarks");
+      return DCORA_ERR_ARG;
+    }
+    H.n[a] = g.n; H.l[a] = g.l; H.b[a] = g.b;
+    const int64_t k = (int64_t)dh * g.n + g.l + g.b;
+    H.coff[a + 1] = H.coff[a] + k;
+    H.poff[a + 1] = H.poff[a] + g.n;
+    H.nnz_in += g.rowptr[k];
+  }
+  H.K = H.coff[A];
+  H.np = H.poff[A];
+  if (H.K * (int64_t)MAX_RANK >= ((int64_t)1 << 31) * 8) {
+    set_error("build_layout: problem dimension exceeds indexing range");
+    return DCORA_ERR_ARG;
+  }
+  if (H.K >= ((int64_t)1 << 31)) {
+    set_error("build_layout: K exceeds int32");
+    return DCORA_ERR_ARG;
+  }
+  std::vector<AgentLayout> AL(A);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int a = 0; a < A; ++a) convert_agent(agents[a], d, order, &AL[a]);
+  for (int a = 0; a < A; ++a)
+    if (AL[a].rc != DCORA_OK) {
+      set_error("build_layout: column index out of range");
+      return AL[a].rc;
+    }
+
+  // ---- merge
+  H.identity_perm = (order == DCORA_ORDER_SE);
+  H.perm.resize(H.K);
+  H.prowcol.resize(H.np);
+  H.browptr.assign(H.np + 1, 0);
+  size_t nnzb = 0, nrow = 0, nrem = 0;
+  for (int a = 0; a < A; ++a) {
+    nnzb += AL[a].bcol.size();
+    nrow += AL[a].rem_row.size();
+    nrem += AL[a].rem_col.size();
+  }
+  H.bcol.resize(nnzb);
+  H.bval.resize(nnzb * dh * dh);
+  H.rem_row.resize(nrow); H.rem_assign.resize(nrow);
+  H.rem_rowptr.assign(nrow + 1, 0);
+  H.rem_col.resize(nrem); H.rem_val.resize(nrem);
+  size_t ob = 0, orow = 0, orem = 0;
+  for (int a = 0; a < A; ++a) {
+    const AgentLayout &L = AL[a];
+    const int c0 = (int)H.coff[a];
+    const int k = (int)(H.coff[a + 1] - H.coff[a]);
+    for (int c = 0; c < k; ++c) H.perm[c0 + L.m[c]] = c0 + c;
+    for (int i = 0; i < H.n[a]; ++i) {
+      H.prowcol[H.poff[a] + i] = c0 + i * dh;
+      H.browptr[H.poff[a] + i + 1] = (int)ob + L.browptr[i + 1];
+    }
+    for (size_t q = 0; q < L.bcol.size(); ++q) H.bcol[ob + q] = c0 + L.bcol[q] * dh;
+    std::copy(L.bval.begin(), L.bval.end(), H.bval.begin() + ob * dh * dh);
+    for (size_t q = 0; q < L.rem_row.size(); ++q) {
+      H.rem_row[orow + q] = c0 + L.rem_row[q];
+      H.rem_assign[orow + q] = L.rem_assign[q];
+      H.rem_rowptr[orow + q + 1] = (int)orem + L.rem_rowptr[q + 1];
+    }
+    for (size_t q = 0; q < L.rem_col.size(); ++q) {
+      H.rem_col[orem + q] = c0 + L.rem_col[q];
+      H.rem_val[orem + q] = L.rem_val[q];
+    }
+    ob += L.bcol.size(); orow += L.rem_row.size(); orem += L.rem_col.size();
+  }
+
+  // ---- chunk table
+  H.chunks.clear();
+  H.agent_chunk0.assign(A + 1, 0);
+  for (int a = 0; a < A; ++a) {
+    H.agent_chunk0[a] = (int)H.chunks.size();
+    const int c0 = (int)H.coff[a];
+    for (int i = 0; i < H.n[a]; i += POSE_CHUNK) {
+      const int np = std::min(POSE_CHUNK, H.n[a] - i);
+      H.chunks.push_back({c0 + i * dh, np * dh, KIND_POSE, a});
+    }
+    int base = c0 + dh * H.n[a];
+    for (int i = 0; i < H.l[a]; i += EXTRA_CHUNK)
+      H.chunks.push_back({base + i, std::min(EXTRA_CHUNK, H.l[a] - i), KIND_SPHERE, a});
+    base += H.l[a];
+    for (int i = 0; i < H.b[a]; i += EXTRA_CHUNK)
+      H.chunks.push_back({base + i, std::min(EXTRA_CHUNK, H.b[a] - i), KIND_EUCLID, a});
+  }
+  H.agent_chunk0[A] = (int)H.chunks.size();
+  return DCORA_OK;
+}
+
+}  // namespace dcora

@@ -1,0 +1,453 @@
+// Handle life-cycle, host<->device staging, and the QuadraticProblem-level
+// entry points of the C-ABI (include/dcora_b200.h).
+#include <omp.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "kernels.cuh"
+#include "solver.cuh"
+
+namespace dcora {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+DeviceMatrices::~DeviceMatrices() {
+  cudaSetDevice(device);
+  cudaFree(perm); cudaFree(browptr); cudaFree(bcol); cudaFree(prowcol);
+  cudaFree(pose_agent); cudaFree(rem_agent); cudaFree(bval);
+  cudaFree(rem_row); cudaFree(rem_rowptr); cudaFree(rem_col);
+  cudaFree(rem_assign); cudaFree(rem_val); cudaFree(chunks); cudaFree(agent_chunk0);
+  F.release();
+}
+
+template <typename T>
+static cudaError_t upload(T **dst, const std::vector<T> &src) {
+  cudaError_t e = cudaMalloc(dst, std::max<size_t>(1, src.size()) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (src.empty()) return cudaSuccess;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static bool is_device_ptr(const void *ptr) {
+  if (!ptr) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Bring a reference-layout r x K matrix (host or device) into the internal
+// layout vector `dst` (device).
+int import_matrix(dcora_problem *p, const double *src, double *dst, int r) {
+  DeviceMatrices &M = *p->M;
+  const size_t bytes = (size_t)M.K * r * sizeof(double);
+  const bool dev = is_device_ptr(src);
+  if (M.identity_perm) {
+    if (src != dst)
+      DCORA_CUDA(cudaMemcpyAsync(dst, src, bytes,
+                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                 p->stream));
+    return DCORA_OK;
+  }
+  const double *s = src;
+  if (!dev) {
+    DCORA_CUDA(cudaMemcpyAsync(p->stage, src, bytes, cudaMemcpyHostToDevice, p->stream));
+    s = p->stage;
+  }
+  return launch_permute(p, s, dst, r, true);
+}
+
+int export_matrix(dcora_problem *p, const double *src, double *dst, int r) {
+  DeviceMatrices &M = *p->M;
+  const size_t bytes = (size_t)M.K * r * sizeof(double);
+  const bool dev = is_device_ptr(dst);
+  if (M.identity_perm) {
+    if (src != dst)
+      DCORA_CUDA(cudaMemcpyAsync(dst, src, bytes,
+                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                 p->stream));
+  } else if (dev) {
+    DCORA_TRY(launch_permute(p, src, dst, r, false));
+  } else {
+    DCORA_TRY(launch_permute(p, src, p->stage, r, false));
+    DCORA_CUDA(cudaMemcpyAsync(dst, p->stage, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  if (!dev) DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+int read_scalars(dcora_problem *p) {
+  DCORA_CUDA(cudaMemcpyAsync(p->h_scal, p->scal, sizeof(double) * NS * p->M->A,
+                             cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaMemcpyAsync(p->h_flags, p->flags, sizeof(int) * NF * p->M->A,
+                             cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+static int alloc_handle_buffers(dcora_problem *p) {
+  DeviceMatrices &M = *p->M;
+  p->vec_len = (size_t)M.K * p->r;
+  p->ws.assign(WS_COUNT, nullptr);
+  DCORA_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  DCORA_CUDA(cudaMalloc(&p->G, std::max<size_t>(1, p->vec_len) * sizeof(double)));
+  DCORA_CUDA(cudaMemsetAsync(p->G, 0, p->vec_len * sizeof(double), p->stream));
+  if (!M.identity_perm)
+    DCORA_CUDA(cudaMalloc(&p->stage, std::max<size_t>(1, p->vec_len) * sizeof(double)));
+  DCORA_CUDA(cudaMalloc(&p->partials, std::max(1, M.nchunks) * NPART * sizeof(double)));
+  DCORA_CUDA(cudaMalloc(&p->scal, sizeof(double) * NS * M.A));
+  DCORA_CUDA(cudaMalloc(&p->flags, sizeof(int) * (NF * M.A + 4)));  // + counters
+  DCORA_CUDA(cudaMallocHost(&p->h_scal, sizeof(double) * NS * M.A));
+  DCORA_CUDA(cudaMallocHost(&p->h_flags, sizeof(int) * (NF * M.A + 4)));
+  DCORA_CUDA(cudaMemsetAsync(p->scal, 0, sizeof(double) * NS * M.A, p->stream));
+  std::vector<int> fl((size_t)NF * M.A + 4, 0);
+  for (int a = 0; a < M.A; ++a) { fl[a * NF + F_ALL] = 1; fl[a * NF + F_USER] = 1; }
+  DCORA_CUDA(cudaMemcpyAsync(p->flags, fl.data(), fl.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+}  // namespace dcora
+
+using namespace dcora;
+
+double *dcora_problem::vec(int i) {
+  if (i < 0 || i >= (int)ws.size()) return nullptr;
+  if (!ws[i]) {
+    if (cudaMalloc(&ws[i], std::max<size_t>(1, vec_len) * sizeof(double)) != cudaSuccess) {
+      set_error("workspace allocation failed");
+      ws[i] = nullptr;
+    }
+  }
+  return ws[i];
+}
+
+dcora_problem::~dcora_problem() {
+  if (M) cudaSetDevice(M->device);
+  for (double *w : ws) cudaFree(w);
+  cudaFree(G); cudaFree(stage); cudaFree(partials); cudaFree(scal); cudaFree(flags);
+  cudaFreeHost(h_scal); cudaFreeHost(h_flags);
+  if (stream && owns_stream) cudaStreamDestroy(stream);
+}
+
+extern "C" {
+
+const char *dcora_last_error(void) { return g_error.c_str(); }
+
+int dcora_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void dcora_ropt_params_default(dcora_ropt_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->method = 0;
+  p->verbose = 0;
+  p->gradnorm_tol = 1e-2;
+  p->RGD_stepsize = 1e-3;
+  p->RGD_use_preconditioner = 1;
+  p->RTR_iterations = 3;
+  p->RTR_tCG_iterations = 50;
+  p->RTR_initial_radius = 100;
+  p->time_bound_s = 5.0;
+  p->retraction = DCORA_RETRACT_QF;
+}
+
+int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
+                         int32_t r, int32_t d, int32_t order, int32_t device,
+                         dcora_problem **out) {
+  if (!out) return DCORA_ERR_ARG;
+  *out = nullptr;
+  if (dcora_device_count() <= device || device < 0) {
+    set_error("no CUDA device " + std::to_string(device) +
+              " (the dcora_b200 hot path has no CPU fallback)");
+    return DCORA_ERR_CUDA;
+  }
+  DCORA_CUDA(cudaSetDevice(device));
+  HostLayout H;
+  DCORA_TRY(build_layout(agents, num_agents, r, d, order, &H));
+  auto M = std::make_shared<DeviceMatrices>();
+  M->device = device;
+  M->d = d; M->order = order; M->A = H.A; M->np = H.np; M->K = H.K;
+  M->nnz_in = H.nnz_in;
+  M->nnzb = (int64_t)H.bcol.size();
+  M->nrem_rows = (int64_t)H.rem_row.size();
+  M->nrem = (int64_t)H.rem_col.size();
+  M->nchunks = (int)H.chunks.size();
+  M->coff = H.coff; M->n = H.n; M->l = H.l; M->b = H.b; M->poff = H.poff;
+  M->agent_chunk0_h = H.agent_chunk0;
+  M->identity_perm = H.identity_perm;
+  std::vector<int> pose_agent(H.np), rem_agent(H.rem_row.size());
+  for (int a = 0; a < H.A; ++a)
+    for (int i = H.poff[a]; i < H.poff[a + 1]; ++i) pose_agent[i] = a;
+  {
+    int a = 0;
+    for (size_t s = 0; s < H.rem_row.size(); ++s) {
+      while (H.rem_row[s] >= H.coff[a + 1]) ++a;
+      rem_agent[s] = a;
+    }
+  }
+  DCORA_CUDA(upload(&M->perm, H.perm));
+  DCORA_CUDA(upload(&M->browptr, H.browptr));
+  DCORA_CUDA(upload(&M->bcol, H.bcol));
+  DCORA_CUDA(upload(&M->bval, H.bval));
+  DCORA_CUDA(upload(&M->prowcol, H.prowcol));
+  DCORA_CUDA(upload(&M->pose_agent, pose_agent));
+  DCORA_CUDA(upload(&M->rem_agent, rem_agent));
+  DCORA_CUDA(upload(&M->rem_row, H.rem_row));
+  DCORA_CUDA(upload(&M->rem_rowptr, H.rem_rowptr));
+  DCORA_CUDA(upload(&M->rem_col, H.rem_col));
+  DCORA_CUDA(upload(&M->rem_val, H.rem_val));
+  DCORA_CUDA(upload(&M->rem_assign, H.rem_assign));
+  DCORA_CUDA(upload(&M->chunks, H.chunks));
+  DCORA_CUDA(upload(&M->agent_chunk0, H.agent_chunk0));
+
+  // ---- preconditioner factors (host) -> device
+  bool any = false;
+  for (int a = 0; a < num_agents; ++a) any = any || agents[a].precond_reg >= 0.0;
+  if (any) {
+    std::vector<HostFactor> HF(num_agents);
+    std::vector<int> rcs(num_agents, DCORA_OK);
+    const int dh = d + 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int a = 0; a < num_agents; ++a) {
+      const dcora_agent_desc &g = agents[a];
+      const int k = dh * g.n + g.l + g.b;
+      // P = Q + reg I in the agent-local internal ordering (full symmetric CSR)
+      const int c0 = (int)H.coff[a];
+      std::vector<int> ref2int(k);
+      for (int c = 0; c < k; ++c) ref2int[H.perm[c0 + c] - c0] = c;
+      // H.perm: internal -> reference; invert
+      std::vector<int> Ap(k + 1, 0);
+      for (int R = 0; R < k; ++R) Ap[ref2int[R] + 1] = g.rowptr[R + 1] - g.rowptr[R] + 1;
+      for (int i = 0; i < k; ++i) Ap[i + 1] += Ap[i];
+      std::vector<int> Ai(Ap[k]);
+      std::vector<double> Ax(Ap[k]);
+      const double reg = g.precond_reg >= 0.0 ? g.precond_reg : 0.0;
+      for (int R = 0; R < k; ++R) {
+        const int ri = ref2int[R];
+        int w = Ap[ri];
+        bool diag = false;
+        for (int q = g.rowptr[R]; q < g.rowptr[R + 1]; ++q) {
+          const int ci = ref2int[g.col[q]];
+          double v = g.val[q];
+          if (ci == ri) { v += reg; diag = true; }
+          Ai[w] = ci; Ax[w] = v; ++w;
+        }
+        if (!diag) { Ai[w] = ri; Ax[w] = reg; ++w; }
+        // unused slot (diag present): mark with a harmless zero on the diagonal
+        if (w < Ap[ri + 1]) { Ai[w] = ri; Ax[w] = 0.0; }
+      }
+      // symmetrise numerically: P <- (P + P^T)/2 is implied by using the upper
+      // triangle only inside sparse_cholesky (as CHOLMOD does for symmetric
+      // input).
+      rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a]);
+    }
+    for (int a = 0; a < num_agents; ++a)
+      if (rcs[a] != DCORA_OK) {
+        set_error("Cholesky factorisation of Q + reg*I failed for agent " + std::to_string(a));
+        return DCORA_ERR_FACTOR;
+      }
+    DCORA_TRY(upload_factor(M.get(), HF, H));
+  }
+
+  dcora_problem *p = new dcora_problem();
+  p->r = r;
+  p->M = M;
+  int rc = alloc_handle_buffers(p);
+  if (rc != DCORA_OK) { delete p; return rc; }
+  // linear term
+  bool anyG = false;
+  for (int a = 0; a < num_agents; ++a) anyG = anyG || agents[a].G != nullptr;
+  if (anyG) {
+    std::vector<double> Gh((size_t)H.K * r, 0.0);
+    for (int a = 0; a < num_agents; ++a)
+      if (agents[a].G)
+        std::memcpy(&Gh[(size_t)H.coff[a] * r], agents[a].G,
+                    sizeof(double) * (size_t)(H.coff[a + 1] - H.coff[a]) * r);
+    rc = dcora_problem_set_G(p, Gh.data());
+    if (rc != DCORA_OK) { delete p; return rc; }
+  }
+  *out = p;
+  return DCORA_OK;
+}
+
+int dcora_problem_clone_rank(const dcora_problem *src, int32_t r, dcora_problem **out) {
+  if (!src || !out || r < 1 || r > MAX_RANK) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(src->M->device));
+  dcora_problem *p = new dcora_problem();
+  p->r = r;
+  p->M = src->M;
+  int rc = alloc_handle_buffers(p);
+  if (rc != DCORA_OK) { delete p; return rc; }
+  *out = p;
+  return DCORA_OK;
+}
+
+void dcora_problem_destroy(dcora_problem *p) { delete p; }
+
+int64_t dcora_problem_dim(const dcora_problem *p) { return p ? p->M->K : 0; }
+int32_t dcora_problem_rank(const dcora_problem *p) { return p ? p->r : 0; }
+int32_t dcora_problem_num_agents(const dcora_problem *p) { return p ? p->M->A : 0; }
+int64_t dcora_problem_nnz(const dcora_problem *p) { return p ? p->M->nnz_in : 0; }
+int64_t dcora_problem_factor_nnz(const dcora_problem *p) { return p ? p->M->F.nnzL : 0; }
+void *dcora_problem_stream(const dcora_problem *p) { return p ? (void *)p->stream : nullptr; }
+int64_t dcora_problem_launch_count(const dcora_problem *p) { return p ? p->launches : 0; }
+
+#define DCORA_ENTER(p)                         \
+  if (!(p)) return DCORA_ERR_ARG;              \
+  DCORA_CUDA(cudaSetDevice((p)->M->device));
+
+int dcora_problem_set_G(dcora_problem *p, const double *G) {
+  DCORA_ENTER(p);
+  if (!G) {
+    DCORA_CUDA(cudaMemsetAsync(p->G, 0, p->vec_len * sizeof(double), p->stream));
+    p->has_G = false;
+    return DCORA_OK;
+  }
+  DCORA_TRY(import_matrix(p, G, p->G, p->r));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  p->has_G = true;
+  return DCORA_OK;
+}
+
+// f_a = 0.5 <X Q, X> + <X, G> per agent -> scal slot `slot`
+static int compute_f(dcora_problem *p, const double *X, double *tmp, int slot, int mask) {
+  DCORA_TRY(launch_spmm(p, X, nullptr, tmp, mask));
+  const double *xs[2] = {tmp, X};
+  const double *ys[2] = {X, p->G};
+  DCORA_TRY(launch_dots(p, p->has_G ? 2 : 1, xs, ys, mask));
+  return launch_combine_f(p, slot, p->has_G ? 1 : 0, mask);
+}
+
+int dcora_problem_f(dcora_problem *p, const double *X, double *f_out) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
+  if (!x || !t) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(compute_f(p, x, t, S_TMP0, F_ALL));
+  DCORA_TRY(read_scalars(p));
+  for (int a = 0; a < p->M->A; ++a) f_out[a] = p->h_scal[a * NS + S_TMP0];
+  return DCORA_OK;
+}
+
+int dcora_problem_egrad(dcora_problem *p, const double *X, double *EG) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
+  if (!x || !t) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(launch_spmm(p, x, p->has_G ? p->G : nullptr, t, -1));
+  return export_matrix(p, t, EG, p->r);
+}
+
+int dcora_problem_hessvec(dcora_problem *p, const double *V, double *HV) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
+  if (!x || !t) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, V, x, p->r));
+  DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
+  return export_matrix(p, t, HV, p->r);
+}
+
+int dcora_problem_precond(dcora_problem *p, const double *X, const double *V,
+                          double *OUT) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *v = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !v || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(import_matrix(p, V, v, p->r));
+  DCORA_TRY(launch_precond(p, x, v, o, -1));
+  return export_matrix(p, o, OUT, p->r);
+}
+
+int dcora_problem_rgrad(dcora_problem *p, const double *X, double *RG) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !t || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(launch_spmm(p, x, p->has_G ? p->G : nullptr, t, -1));
+  DCORA_TRY(launch_project_tangent(p, x, t, o, -1));
+  return export_matrix(p, o, RG, p->r);
+}
+
+int dcora_problem_rgradnorm(dcora_problem *p, const double *X, double *norm_out) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !t || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(launch_spmm(p, x, p->has_G ? p->G : nullptr, t, -1));
+  DCORA_TRY(launch_project_tangent(p, x, t, o, -1));
+  const double *xs[1] = {o};
+  DCORA_TRY(launch_dots(p, 1, xs, xs, -1));
+  const int dst[1] = {S_TMP0};
+  DCORA_TRY(launch_reduce_scalars(p, 1, dst));
+  DCORA_TRY(read_scalars(p));
+  for (int a = 0; a < p->M->A; ++a) norm_out[a] = std::sqrt(p->h_scal[a * NS + S_TMP0]);
+  return DCORA_OK;
+}
+
+int dcora_problem_retract(dcora_problem *p, const double *X, const double *V,
+                          double *Xout, int32_t retraction) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *v = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !v || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(import_matrix(p, V, v, p->r));
+  DCORA_TRY(launch_retract(p, x, v, o, retraction, -1));
+  return export_matrix(p, o, Xout, p->r);
+}
+
+int dcora_problem_project_tangent(dcora_problem *p, const double *X, const double *V,
+                                  double *OUT) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *v = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !v || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(import_matrix(p, V, v, p->r));
+  DCORA_TRY(launch_project_tangent(p, x, v, o, -1));
+  return export_matrix(p, o, OUT, p->r);
+}
+
+int dcora_problem_project_manifold(dcora_problem *p, const double *Mx, double *OUT) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *o = p->vec(WS_IO2);
+  if (!x || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, Mx, x, p->r));
+  DCORA_TRY(launch_project_manifold(p, x, o, -1));
+  return export_matrix(p, o, OUT, p->r);
+}
+
+int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
+                            double *algorithmic_bytes) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
+  if (!x || !t) return DCORA_ERR_ALLOC;
+  cudaEvent_t e0, e1;
+  DCORA_CUDA(cudaEventCreate(&e0));
+  DCORA_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
+  DCORA_CUDA(cudaEventRecord(e0, p->stream));
+  for (int i = 0; i < iters; ++i) DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
+  DCORA_CUDA(cudaEventRecord(e1, p->stream));
+  DCORA_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DCORA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_mean) *ms_mean = (double)ms / std::max(1, iters);
+  if (algorithmic_bytes)
+    *algorithmic_bytes = 8.0 * (double)p->M->nnz_in + 16.0 * (double)p->r * (double)p->M->K;
+  return DCORA_OK;
+}
+
+}  // extern "C"

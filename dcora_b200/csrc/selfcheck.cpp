@@ -1,0 +1,105 @@
+// Host-only self checks of the setup code (layout conversion, sparse
+// Cholesky).  They return an error norm on internally generated data; they do
+// not produce results a caller could use instead of the GPU path.
+#include <cmath>
+#include <cstdint>
+
+#include "common.cuh"
+
+using namespace dcora;
+
+static inline double prand(uint64_t &st) {
+  st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+  return (double)(st >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+extern "C" int dcora_selfcheck_layout(const dcora_agent_desc *agents, int32_t num_agents,
+                                      int32_t r, int32_t d, int32_t order,
+                                      double *max_abs_err) {
+  HostLayout H;
+  DCORA_TRY(build_layout(agents, num_agents, r, d, order, &H));
+  const int dh = d + 1;
+  uint64_t st = 88172645463325252ull;
+  std::vector<double> Xref((size_t)H.K * r), Xint((size_t)H.K * r);
+  for (auto &v : Xref) v = prand(st);
+  for (int64_t c = 0; c < H.K; ++c)
+    for (int q = 0; q < r; ++q) Xint[c * r + q] = Xref[(size_t)H.perm[c] * r + q];
+  // reference: Y = X * Q per agent from the CSR as given
+  std::vector<double> Yref((size_t)H.K * r, 0.0), Yint((size_t)H.K * r, 0.0);
+  for (int a = 0; a < num_agents; ++a) {
+    const dcora_agent_desc &g = agents[a];
+    const int64_t c0 = H.coff[a];
+    const int k = (int)(H.coff[a + 1] - c0);
+    for (int R = 0; R < k; ++R)
+      for (int p = g.rowptr[R]; p < g.rowptr[R + 1]; ++p)
+        for (int q = 0; q < r; ++q)
+          Yref[(c0 + g.col[p]) * r + q] += Xref[(c0 + R) * r + q] * g.val[p];
+  }
+  // converted structures, same arithmetic the kernels perform
+  for (int i = 0; i < H.np; ++i)
+    for (int p = H.browptr[i]; p < H.browptr[i + 1]; ++p)
+      for (int a = 0; a < dh; ++a)
+        for (int b = 0; b < dh; ++b)
+          for (int q = 0; q < r; ++q)
+            Yint[(size_t)(H.prowcol[i] + a) * r + q] +=
+                H.bval[(size_t)p * dh * dh + a * dh + b] * Xint[(size_t)(H.bcol[p] + b) * r + q];
+  for (size_t s = 0; s < H.rem_row.size(); ++s)
+    for (int p = H.rem_rowptr[s]; p < H.rem_rowptr[s + 1]; ++p)
+      for (int q = 0; q < r; ++q)
+        Yint[(size_t)H.rem_row[s] * r + q] += H.rem_val[p] * Xint[(size_t)H.rem_col[p] * r + q];
+  double err = 0.0;
+  for (int64_t c = 0; c < H.K; ++c)
+    for (int q = 0; q < r; ++q)
+      err = std::fmax(err, std::fabs(Yint[c * r + q] - Yref[(size_t)H.perm[c] * r + q]));
+  // chunk table must tile [0, K) exactly
+  int64_t next = 0;
+  for (const Chunk &ch : H.chunks) {
+    if (ch.col0 != next) err = INFINITY;
+    next += ch.ncols;
+  }
+  if (next != H.K) err = INFINITY;
+  if (max_abs_err) *max_abs_err = err;
+  return DCORA_OK;
+}
+
+extern "C" int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const int32_t *col,
+                                        const double *val, int32_t dh, int32_t npose,
+                                        double reg, double *rel_residual,
+                                        int64_t *factor_nnz) {
+  std::vector<int> Ap(rowptr, rowptr + k + 1), Ai;
+  std::vector<double> Ax;
+  // append reg on the diagonal (an explicit extra entry per row)
+  std::vector<int> Bp(k + 1, 0);
+  for (int i = 0; i < k; ++i) Bp[i + 1] = Bp[i] + (Ap[i + 1] - Ap[i]) + 1;
+  Ai.resize(Bp[k]); Ax.resize(Bp[k]);
+  for (int i = 0; i < k; ++i) {
+    int w = Bp[i];
+    for (int p = Ap[i]; p < Ap[i + 1]; ++p) { Ai[w] = col[p]; Ax[w] = val[p]; ++w; }
+    Ai[w] = i; Ax[w] = reg;
+  }
+  HostFactor F;
+  DCORA_TRY(sparse_cholesky(k, Bp, Ai, Ax, dh, npose, &F));
+  if (factor_nnz) *factor_nnz = (int64_t)F.Lx.size();
+  uint64_t st = 1234567ull;
+  std::vector<double> b(k), y(k), x(k);
+  for (auto &v : b) v = prand(st);
+  for (int i = 0; i < k; ++i) y[i] = b[F.perm[i]];
+  for (int j = 0; j < k; ++j) {           // L y = Pb (column oriented)
+    y[j] /= F.Lx[F.Lp[j]];
+    for (int p = F.Lp[j] + 1; p < F.Lp[j + 1]; ++p) y[F.Li[p]] -= F.Lx[p] * y[j];
+  }
+  for (int j = k - 1; j >= 0; --j) {      // L^T z = y
+    for (int p = F.Lp[j] + 1; p < F.Lp[j + 1]; ++p) y[j] -= F.Lx[p] * y[F.Li[p]];
+    y[j] /= F.Lx[F.Lp[j]];
+  }
+  for (int i = 0; i < k; ++i) x[F.perm[i]] = y[i];
+  double rn = 0.0, bn = 0.0;
+  for (int i = 0; i < k; ++i) {
+    double s = reg * x[i];
+    for (int p = Ap[i]; p < Ap[i + 1]; ++p) s += val[p] * x[col[p]];
+    rn += (s - b[i]) * (s - b[i]);
+    bn += b[i] * b[i];
+  }
+  if (rel_residual) *rel_residual = std::sqrt(rn / bn);
+  return DCORA_OK;
+}

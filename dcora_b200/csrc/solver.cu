@@ -1,0 +1,463 @@
+// K3/K4: Riemannian trust-region (RTR) with truncated CG, run for a whole batch
+// of agents at once on the device.
+//
+// Replaces ROPTLIB::RTRNewton::Run / SolversTR::tCG_TR as driven by
+// QuadraticOptimizer (src/QuadraticOptimizer.cpp:28-108,234-280).  ROPTLIB is
+// not vendored in the reference tree (cmake/roptlib.cmake:7-8 fetches
+// yuluntian/ROPTLIB@feature/cmake); the algorithm is restated from upstream:
+// theta = 1, kappa = 0.1, Acceptence_Rho = 0.1, Shrinked_tau = 0.25,
+// Magnified_tau = 2, radius measured in the preconditioner norm.
+//
+// Every agent keeps its own trust-region state in p->scal / p->flags; vector
+// kernels are masked per agent, so agents converge independently while sharing
+// launches.  The host only reads back two counters per iteration.
+#include <chrono>
+#include <cmath>
+
+#include "solver.cuh"
+
+namespace dcora {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum of partial slot `slot` over agent a's chunks (fixed order); valid in
+// every thread of the 128-thread CTA.
+__device__ double agent_sum(const int *agent_chunk0, const double *partials, int a,
+                            int slot, double *sm) {
+  const int c0 = agent_chunk0[a], c1 = agent_chunk0[a + 1];
+  double acc = 0.0;
+  for (int c = c0 + threadIdx.x; c < c1; c += 128) acc += partials[(size_t)c * NPART + slot];
+  acc = warp_sum(acc);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  return sm[0] + sm[1] + sm[2] + sm[3];
+}
+
+__global__ void __launch_bounds__(128)
+combine_f_kernel(const int *agent_chunk0, const double *partials, const int *flags,
+                 int mask_flag, int slot, int with_G, double *scal) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  if (mask_flag >= 0 && flags[a * NF + mask_flag] == 0) return;
+  const double p0 = agent_sum(agent_chunk0, partials, a, 0, sm);
+  const double p1 = with_G ? agent_sum(agent_chunk0, partials, a, 1, sm) : 0.0;
+  if (threadIdx.x == 0) scal[a * NS + slot] = 0.5 * p0 + p1;
+}
+
+// after f1 (S_F1) and <gf,gf> (partial 0)
+__global__ void __launch_bounds__(128)
+rtr_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
+                double *scal, double tol, double delta0, double max_delta,
+                int *counters) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  const double gg = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  int *f = flags + a * NF;
+  const double ngf = sqrt(gg);
+  s[S_NGF] = ngf;
+  s[S_FINIT] = s[S_F1];
+  s[S_GNINIT] = ngf;
+  s[S_DELTA] = delta0;
+  s[S_MAXDELTA] = max_delta;
+  s[S_TOL] = tol;
+  // QuadraticOptimizer::trustRegion early return (:54)
+  const int on = f[F_USER] != 0 && !(ngf < tol);
+  f[F_OUTER] = on;
+  f[F_TCG] = 0; f[F_STEP] = 0; f[F_END] = 0;
+  f[F_STATUS] = DCORA_TCG_MAXITER;
+  f[F_NINNER] = 0; f[F_NOUTER] = 0; f[F_ACCEPT] = 0;
+  if (on) atomicAdd(&counters[0], 1);
+}
+
+// start of tCG: partial 0 = <z, r>
+__global__ void __launch_bounds__(128)
+tcg_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
+                double *scal) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  int *f = flags + a * NF;
+  if (f[F_OUTER] == 0) { if (threadIdx.x == 0) f[F_TCG] = 0; return; }
+  const double zr = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  s[S_ZR] = zr; s[S_DPD] = zr; s[S_EPE] = 0.0; s[S_EPD] = 0.0;
+  s[S_NR0] = s[S_NGF];
+  f[F_TCG] = 1; f[F_STEP] = 0; f[F_END] = 0;
+  f[F_STATUS] = DCORA_TCG_MAXITER;
+}
+
+// partial 0 = <delta, H delta>
+__global__ void __launch_bounds__(128)
+tcg_stepA_kernel(const int *agent_chunk0, const double *partials, int *flags,
+                 double *scal) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  int *f = flags + a * NF;
+  if (f[F_TCG] == 0) { if (threadIdx.x == 0) f[F_STEP] = 0; return; }
+  const double d_Hd = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  const double z_r = s[S_ZR], d_Pd = s[S_DPD], e_Pd = s[S_EPD], e_Pe = s[S_EPE];
+  const double Delta = s[S_DELTA];
+  const double alpha = z_r / d_Hd;
+  const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+  s[S_DHD] = d_Hd;
+  f[F_STEP] = 1;
+  if (d_Hd <= 0.0 || e_Pe_new >= Delta * Delta) {
+    const double tau =
+        (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
+    s[S_CETA] = tau;
+    s[S_CR] = 0.0;
+    f[F_STATUS] = d_Hd <= 0.0 ? DCORA_TCG_NEGCURVTURE : DCORA_TCG_EXCREGION;
+    f[F_END] = 1;
+  } else {
+    s[S_EPE] = e_Pe_new;
+    s[S_ALPHA] = alpha;
+    s[S_CETA] = alpha;
+    s[S_CR] = alpha;
+    f[F_END] = 0;
+  }
+}
+
+// partial 0 = <r, r> after the update
+__global__ void __launch_bounds__(128)
+tcg_stepB_kernel(const int *agent_chunk0, const double *partials, int *flags,
+                 double *scal, int j, int min_inner, int max_inner, int *counters) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  int *f = flags + a * NF;
+  if (f[F_STEP] == 0) return;
+  const double rr = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  f[F_NINNER] += 1;
+  int on = 1;
+  if (f[F_END]) {
+    on = 0;
+  } else {
+    const double nr = sqrt(rr), nr0 = s[S_NR0];
+    s[S_NR] = nr;
+    const double theta = 1.0, kappa = 0.1;
+    const double pw = pow(nr0, theta);
+    if (j >= min_inner && nr <= nr0 * (pw < kappa ? pw : kappa)) {
+      f[F_STATUS] = kappa < pw ? DCORA_TCG_LCON : DCORA_TCG_SCON;
+      on = 0;
+    } else if (j + 1 >= max_inner) {
+      on = 0;  // status stays TR_MAXITER
+    }
+  }
+  f[F_TCG] = on;
+  if (on) atomicAdd(&counters[1], 1);
+}
+
+// partial 0 = <z, r> with the new z
+__global__ void __launch_bounds__(128)
+tcg_stepC_kernel(const int *agent_chunk0, const double *partials, const int *flags,
+                 double *scal) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  if (flags[a * NF + F_TCG] == 0) return;
+  const double zr = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  const double zold = s[S_ZR];
+  const double beta = zr / zold;
+  const double alpha = s[S_ALPHA], d_Pd = s[S_DPD], e_Pd = s[S_EPD];
+  s[S_ZR] = zr;
+  s[S_BETA] = beta;
+  s[S_EPD] = beta * (e_Pd + alpha * d_Pd);
+  s[S_DPD] = zr + beta * beta * d_Pd;
+}
+
+// S_F2 holds f(x2); partial 0 = <eta, gf1>, partial 1 = <eta, H eta>
+__global__ void __launch_bounds__(128)
+rtr_rho_kernel(const int *agent_chunk0, const double *partials, int *flags,
+               double *scal, int single_mode) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  int *f = flags + a * NF;
+  if (f[F_OUTER] == 0) { if (threadIdx.x == 0) f[F_ACCEPT] = 0; return; }
+  const double eg = agent_sum(agent_chunk0, partials, a, 0, sm);
+  const double eh = agent_sum(agent_chunk0, partials, a, 1, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  const double f1 = s[S_F1], f2 = s[S_F2];
+  const double rho = (f1 - f2) / (-(eg + 0.5 * eh));
+  s[S_RHO] = rho;
+  double Delta = s[S_DELTA];
+  const int st = f[F_STATUS];
+  if (rho > 0.75) {
+    if (st == DCORA_TCG_EXCREGION || st == DCORA_TCG_NEGCURVTURE)
+      Delta = fmin(2.0 * Delta, s[S_MAXDELTA]);
+  } else if (rho < 0.25) {
+    Delta *= 0.25;
+  }
+  const int acc = (rho > 0.1) ||
+                  (fabs(f1 - f2) / (fabs(f1) + 1.0) < 1.4901161193847656e-08 && f2 < f1);
+  if (single_mode) {
+    // QuadraticOptimizer.cpp:254-273: radius /= 4 after a rejection and
+    // maximum_Delta = initial_Delta = radius for the next Run()
+    if (!acc) { Delta = s[S_MAXDELTA] * 0.25; s[S_MAXDELTA] = Delta; }
+  }
+  s[S_DELTA] = Delta;
+  f[F_ACCEPT] = acc;
+  f[F_NOUTER] += 1;
+}
+
+// after the gradient at the accepted point: partial 0 = <gf, gf>
+__global__ void __launch_bounds__(128)
+rtr_accept_kernel(const int *agent_chunk0, const double *partials, int *flags,
+                  double *scal, int max_iter, int single_mode, int *counters) {
+  __shared__ double sm[4];
+  const int a = blockIdx.x;
+  int *f = flags + a * NF;
+  if (f[F_OUTER] == 0) return;
+  double gg = 0.0;
+  if (f[F_ACCEPT]) gg = agent_sum(agent_chunk0, partials, a, 0, sm);
+  if (threadIdx.x != 0) return;
+  double *s = scal + a * NS;
+  int on = 1;
+  if (f[F_ACCEPT]) {
+    s[S_F1] = s[S_F2];
+    s[S_NGF] = sqrt(gg);
+    if (s[S_NGF] < s[S_TOL]) on = 0;
+    if (single_mode) on = 0;
+  }
+  if (f[F_NOUTER] >= max_iter) on = 0;
+  f[F_OUTER] = on;
+  if (on) atomicAdd(&counters[0], 1);
+}
+
+}  // namespace
+
+int launch_combine_f(dcora_problem *p, int slot, int with_G, int mask_flag) {
+  combine_f_kernel<<<p->M->A, 128, 0, p->stream>>>(p->M->agent_chunk0, p->partials,
+                                                   p->flags, mask_flag, slot, with_G,
+                                                   p->scal);
+  DCORA_LAUNCH_CHECK(p);
+  return DCORA_OK;
+}
+
+int eval_f(dcora_problem *p, const double *X, double *tmp, int slot, int mask_flag) {
+  DCORA_TRY(launch_spmm(p, X, nullptr, tmp, mask_flag));
+  const double *xs[2] = {tmp, X};
+  const double *ys[2] = {X, p->G};
+  DCORA_TRY(launch_dots(p, p->has_G ? 2 : 1, xs, ys, mask_flag));
+  return launch_combine_f(p, slot, p->has_G ? 1 : 0, mask_flag);
+}
+
+static int read_counters(dcora_problem *p, int *out2) {
+  int *dc = p->flags + (size_t)NF * p->M->A;
+  int *hc = p->h_flags + (size_t)NF * p->M->A;
+  DCORA_CUDA(cudaMemcpyAsync(hc, dc, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  out2[0] = hc[0]; out2[1] = hc[1];
+  return DCORA_OK;
+}
+
+static int zero_counter(dcora_problem *p, int which) {
+  int *dc = p->flags + (size_t)NF * p->M->A;
+  DCORA_CUDA(cudaMemsetAsync(dc + which, 0, sizeof(int), p->stream));
+  return DCORA_OK;
+}
+
+// Riemannian Hessian-vector product at x1: out = proj(V*Q - V*sym(Y^T EG))
+static int rhess(dcora_problem *p, const double *x1, const double *S, const double *v,
+                 double *tmp, double *out, int mask) {
+  DCORA_TRY(launch_spmm(p, v, nullptr, tmp, mask));
+  return launch_rhess_correct(p, x1, S, v, tmp, out, mask);
+}
+
+// EG, gf, S at x1 for the agents selected by `mask`; leaves <gf,gf> in partial 0
+static int gradient_at(dcora_problem *p, const double *x1, double *EG, double *gf,
+                       double *S, int mask) {
+  DCORA_TRY(launch_spmm(p, x1, p->has_G ? p->G : nullptr, EG, mask));
+  DCORA_TRY(launch_project_tangent(p, x1, EG, gf, mask));
+  DCORA_TRY(launch_sym_ytg(p, x1, EG, S, mask));
+  const double *xs[1] = {gf};
+  return launch_dots(p, 1, xs, xs, mask);
+}
+
+static int set_user_mask(dcora_problem *p, const uint8_t *active) {
+  const int A = p->M->A;
+  DCORA_CUDA(cudaMemcpyAsync(p->h_flags, p->flags, sizeof(int) * NF * A,
+                             cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  for (int a = 0; a < A; ++a) {
+    p->h_flags[a * NF + F_USER] = active ? (active[a] ? 1 : 0) : 1;
+    p->h_flags[a * NF + F_ALL] = 1;
+  }
+  DCORA_CUDA(cudaMemcpyAsync(p->flags, p->h_flags, sizeof(int) * NF * A,
+                             cudaMemcpyHostToDevice, p->stream));
+  return DCORA_OK;
+}
+
+int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
+                     const uint8_t *active, dcora_ropt_result *results) {
+  DeviceMatrices &M = *p->M;
+  const int A = M.A;
+  double *x2 = p->vec(WS_X2), *EG = p->vec(WS_EG), *gf = p->vec(WS_GF);
+  double *S = p->vec(WS_S), *eta = p->vec(WS_ETA), *delta = p->vec(WS_DELTA);
+  double *Hd = p->vec(WS_HD), *r = p->vec(WS_R), *z = p->vec(WS_Z);
+  double *t0 = p->vec(WS_T0);
+  if (!x2 || !EG || !gf || !S || !eta || !delta || !Hd || !r || !z || !t0)
+    return DCORA_ERR_ALLOC;
+  int *counters = p->flags + (size_t)NF * A;
+  const auto tstart = std::chrono::steady_clock::now();
+  DCORA_TRY(set_user_mask(p, active));
+
+  // initial statistics: fInit, gradNormInit (QuadraticOptimizer.cpp:30-31)
+  DCORA_TRY(eval_f(p, x1, t0, S_F1, F_USER));
+  DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER));
+  DCORA_TRY(zero_counter(p, 0));
+  const int single_mode = prm->RTR_iterations == 1;
+  const int max_outer = single_mode ? 12 : prm->RTR_iterations;
+  const double Delta0 = prm->RTR_initial_radius;
+  rtr_init_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags,
+                                            p->scal, prm->gradnorm_tol, Delta0,
+                                            single_mode ? Delta0 : 5.0 * Delta0,
+                                            counters);
+  DCORA_LAUNCH_CHECK(p);
+  int cnt[2];
+  DCORA_TRY(read_counters(p, cnt));
+  int n_outer = cnt[0];
+
+  if (prm->method == 1) {
+    // one Riemannian gradient-descent step (QuadraticOptimizer.cpp:124-201)
+    const double *g = gf;
+    if (prm->RGD_use_preconditioner) {
+      DCORA_TRY(launch_precond(p, x1, gf, z, F_USER));
+      g = z;
+    }
+    DCORA_TRY(launch_axpby(p, eta, -1, -prm->RGD_stepsize, g, -1, 0.0, nullptr, F_USER));
+    DCORA_TRY(launch_retract(p, x1, eta, x2, prm->retraction, F_USER));
+    DCORA_TRY(launch_copy(p, x1, x2, F_USER));
+    n_outer = 0;
+  }
+
+  for (int it = 0; it < max_outer && n_outer > 0; ++it) {
+    // ---- tCG (SolversTR::tCG_TR), eta0 = 0
+    DCORA_TRY(launch_copy(p, r, gf, F_OUTER));
+    DCORA_TRY(launch_axpby(p, eta, -1, 0.0, gf, -1, 0.0, nullptr, F_OUTER));
+    DCORA_TRY(launch_precond(p, x1, r, z, F_OUTER));
+    {
+      const double *xs[1] = {z}, *ys[1] = {r};
+      DCORA_TRY(launch_dots(p, 1, xs, ys, F_OUTER));
+    }
+    tcg_init_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+    DCORA_LAUNCH_CHECK(p);
+    DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, -1, 0.0, nullptr, F_TCG));
+    int n_tcg = n_outer;
+    for (int j = 0; j < prm->RTR_tCG_iterations && n_tcg > 0; ++j) {
+      DCORA_TRY(rhess(p, x1, S, delta, t0, Hd, F_TCG));
+      {
+        const double *xs[1] = {delta}, *ys[1] = {Hd};
+        DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
+      }
+      tcg_stepA_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+      DCORA_LAUNCH_CHECK(p);
+      DCORA_TRY(launch_axpby(p, eta, -1, 1.0, eta, S_CETA, 1.0, delta, F_STEP));
+      DCORA_TRY(launch_axpby(p, r, -1, 1.0, r, S_CR, 1.0, Hd, F_STEP));
+      {
+        const double *xs[1] = {r};
+        DCORA_TRY(launch_dots(p, 1, xs, xs, F_STEP));
+      }
+      DCORA_TRY(zero_counter(p, 1));
+      tcg_stepB_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags,
+                                                 p->scal, j, 0, prm->RTR_tCG_iterations,
+                                                 counters);
+      DCORA_LAUNCH_CHECK(p);
+      DCORA_TRY(launch_precond(p, x1, r, z, F_TCG));
+      {
+        const double *xs[1] = {z}, *ys[1] = {r};
+        DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
+      }
+      tcg_stepC_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+      DCORA_LAUNCH_CHECK(p);
+      // delta = -z + beta * delta
+      DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, S_BETA, 1.0, delta, F_TCG));
+      DCORA_TRY(read_counters(p, cnt));
+      n_tcg = cnt[1];
+    }
+    // ---- candidate, model decrease, rho (SolversTR::Run)
+    DCORA_TRY(launch_retract(p, x1, eta, x2, prm->retraction, F_OUTER));
+    DCORA_TRY(eval_f(p, x2, t0, S_F2, F_OUTER));
+    DCORA_TRY(rhess(p, x1, S, eta, t0, Hd, F_OUTER));
+    {
+      const double *xs[2] = {eta, eta}, *ys[2] = {gf, Hd};
+      DCORA_TRY(launch_dots(p, 2, xs, ys, F_OUTER));
+    }
+    rtr_rho_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal,
+                                             single_mode);
+    DCORA_LAUNCH_CHECK(p);
+    DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));
+    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT));
+    DCORA_TRY(zero_counter(p, 0));
+    rtr_accept_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal,
+                                                max_outer, single_mode, counters);
+    DCORA_LAUNCH_CHECK(p);
+    DCORA_TRY(read_counters(p, cnt));
+    n_outer = cnt[0];
+    if (prm->time_bound_s > 0.0) {
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count();
+      if (el > prm->time_bound_s) break;
+    }
+  }
+
+  if (prm->method == 1) {
+    // statistics after the RGD step
+    DCORA_TRY(eval_f(p, x1, t0, S_F1, F_USER));
+    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER));
+    const int dst[1] = {S_TMP0};
+    DCORA_TRY(launch_reduce_scalars(p, 1, dst));
+  }
+  DCORA_TRY(read_scalars(p));
+  const double ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tstart).count();
+  if (results) {
+    for (int a = 0; a < A; ++a) {
+      const double *s = p->h_scal + a * NS;
+      const int *f = p->h_flags + a * NF;
+      dcora_ropt_result &R = results[a];
+      R.success = f[F_USER] ? 1 : 0;
+      R.tCGStatus = f[F_STATUS];
+      R.fInit = s[S_FINIT];
+      R.gradNormInit = s[S_GNINIT];
+      R.fOpt = s[S_F1];
+      R.gradNormOpt = prm->method == 1 ? std::sqrt(s[S_TMP0]) : s[S_NGF];
+      R.elapsedMs = ms;
+      R.outer_iterations = f[F_NOUTER];
+      R.inner_iterations = f[F_NINNER];
+      R.accepted = f[F_ACCEPT];
+      R.reserved = 0;
+    }
+  }
+  return DCORA_OK;
+}
+
+}  // namespace dcora
+
+using namespace dcora;
+
+extern "C" int dcora_rtr_solve(dcora_problem *p, const double *X0, double *Xopt,
+                               const dcora_ropt_params *params, const uint8_t *active,
+                               dcora_ropt_result *results) {
+  if (!p || !X0 || !Xopt) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  dcora_ropt_params prm;
+  if (params) prm = *params; else dcora_ropt_params_default(&prm);
+  double *x1 = p->vec(WS_X1);
+  if (!x1) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X0, x1, p->r));
+  DCORA_TRY(rtr_solve_device(p, x1, &prm, active, results));
+  return export_matrix(p, x1, Xopt, p->r);
+}

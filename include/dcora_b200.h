@@ -1,0 +1,223 @@
+/*
+ * dcora_b200 -- C-ABI of the B200-native DCORA Riemannian-staircase hot path.
+ *
+ * Every entry point replaces one piece of the reference's C++ class surface
+ * (adthoms/dcora; citations are path:line in the reference checkout).  The
+ * library is a plain shared object (extern "C", pointers + sizes, no torch /
+ * Eigen types); INTEGRATION.md shows the reference-side shim that binds it.
+ *
+ * Conventions
+ *  - All dense matrices are fp64, COLUMN-MAJOR r x k (Eigen default,
+ *    include/DCORA/DCORA_types.h:34), in the reference column ordering:
+ *      DCORA_ORDER_SE: [Y1 p1 | Y2 p2 | ...]               k=(d+1)n
+ *      DCORA_ORDER_RA: [Y1..Yn | r1..rl | p1..pn | L1..Lb] k=(d+1)n+l+b
+ *    (include/DCORA/manifold/LiftedVariable.h:27-30,148-152).
+ *  - A handle holds a BATCH of `num_agents` independent agent problems
+ *    (block-diagonal Q); dense arguments of a batch are the per-agent
+ *    matrices concatenated in agent order (agent a occupies r*k_a doubles).
+ *    num_agents==1 is the reference's single QuadraticProblem.
+ *  - Dense pointer arguments may be host OR device pointers (detected with
+ *    cudaPointerGetAttributes).  Host pointers are staged through pinned
+ *    memory inside the call; device pointers are used in place (inputs
+ *    already resident in HBM).
+ *  - Return value: 0 ok; <0 hard error (CUDA / allocation / bad argument,
+ *    text in dcora_last_error()); >0 soft failure mirroring the reference's
+ *    bool / std::optional returns.  There is NO CPU fallback: without a CUDA
+ *    device every compute entry point returns DCORA_ERR_CUDA.
+ *  - A handle is not re-entrant; distinct handles may be driven from
+ *    distinct host threads (one CUDA stream per handle).
+ */
+#ifndef DCORA_B200_H_
+#define DCORA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCORA_OK 0
+#define DCORA_ERR_CUDA (-1)
+#define DCORA_ERR_ARG (-2)
+#define DCORA_ERR_ALLOC (-3)
+#define DCORA_ERR_FACTOR (-4) /* Q + reg*I not positive definite */
+#define DCORA_SOFT_FAIL 1
+
+#define DCORA_ORDER_SE 0
+#define DCORA_ORDER_RA 1
+
+#define DCORA_RETRACT_QF 0    /* ROPTLIB Stiefel qf retraction, diag(R)>0 */
+#define DCORA_RETRACT_POLAR 1 /* polar factor (projectToStiefelManifold)  */
+
+/* ROPTLIB::tCGstatusSet as stored in ROPTResult.tCGStatus
+ * (include/DCORA/DCORA_types.h:226). */
+#define DCORA_TCG_NEGCURVTURE 0
+#define DCORA_TCG_EXCREGION 1
+#define DCORA_TCG_LCON 2
+#define DCORA_TCG_SCON 3
+#define DCORA_TCG_MAXITER 4
+
+typedef struct dcora_problem dcora_problem;
+
+/* One agent's data matrices, as Graph hands them to QuadraticProblem:
+ * Graph::quadraticMatrix() (CSR, int32 indices, include/DCORA/DCORA_types.h:36,
+ * src/Graph.cpp:523-528), Graph::linearMatrix() (src/Graph.cpp:535-540) and
+ * the regularisation of Graph::constructPreconditioner (src/Graph.cpp:1901-1917). */
+typedef struct {
+  int32_t n, l, b;        /* poses, unit spheres, landmarks (Graph::n/l/b)     */
+  const int32_t *rowptr;  /* k+1                                                */
+  const int32_t *col;     /* nnz                                                */
+  const double *val;      /* nnz                                                */
+  const double *G;        /* r x k column-major, or NULL for G = 0              */
+  double precond_reg;     /* reg in chol(Q + reg*I); <0 disables the factor     */
+} dcora_agent_desc;
+
+/* ROptParameters (include/DCORA/DCORA_types.h:152-200) + the hard-coded
+ * Solver->TimeBound (src/QuadraticOptimizer.cpp:252) made explicit. */
+typedef struct {
+  int32_t method;             /* 0 = RTR, 1 = RGD                               */
+  int32_t verbose;
+  double gradnorm_tol;        /* 1e-2                                           */
+  double RGD_stepsize;        /* 1e-3                                           */
+  int32_t RGD_use_preconditioner;
+  int32_t RTR_iterations;     /* 3                                              */
+  int32_t RTR_tCG_iterations; /* 50                                             */
+  double RTR_initial_radius;  /* 100                                            */
+  double time_bound_s;        /* 5.0 in the reference; <=0 disables             */
+  int32_t retraction;         /* DCORA_RETRACT_QF / _POLAR                      */
+  int32_t reserved;
+} dcora_ropt_params;
+
+/* ROPTResult (include/DCORA/DCORA_types.h:203-233), one per agent. */
+typedef struct {
+  int32_t success;
+  int32_t tCGStatus;
+  double fInit, gradNormInit, fOpt, gradNormOpt, elapsedMs;
+  int32_t outer_iterations; /* RTR iterations taken                             */
+  int32_t inner_iterations; /* total tCG iterations                             */
+  int32_t accepted;         /* Solver->latestStepAccepted()                     */
+  int32_t reserved;
+} dcora_ropt_result;
+
+void dcora_ropt_params_default(dcora_ropt_params *p);
+const char *dcora_last_error(void);
+/* Number of visible CUDA devices (0 when none / no driver). */
+int dcora_device_count(void);
+
+/* QuadraticProblem::QuadraticProblem(graph) (src/QuadraticProblem.cpp:19-34)
+ * for `num_agents` graphs of common rank r and dimension d.  Uploads Q (as
+ * BSR of (d+1)x(d+1) pose blocks + a scalar CSR remainder), G, and -- when
+ * precond_reg >= 0 -- builds chol(Q_a + reg*I) on the host (own sparse
+ * Cholesky; replaces Eigen::CholmodDecomposition, src/Graph.cpp:1910-1911)
+ * and uploads the level-scheduled factor. */
+int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
+                         int32_t r, int32_t d, int32_t order, int32_t device,
+                         dcora_problem **out);
+void dcora_problem_destroy(dcora_problem *p);
+
+/* Same Q / factor at another relaxation rank (the staircase re-creates the
+ * Graph per rank but Q does not depend on r: SURVEY 8(a17)).  Shares the
+ * device matrices of `src`. */
+int dcora_problem_clone_rank(const dcora_problem *src, int32_t r,
+                             dcora_problem **out);
+
+int64_t dcora_problem_dim(const dcora_problem *p);      /* K = sum_a k_a     */
+int32_t dcora_problem_rank(const dcora_problem *p);
+int32_t dcora_problem_num_agents(const dcora_problem *p);
+int64_t dcora_problem_nnz(const dcora_problem *p);      /* nnz(Q) as given   */
+int64_t dcora_problem_factor_nnz(const dcora_problem *p);
+/* cudaStream_t the handle launches on (for CUDA-event timing by callers). */
+void *dcora_problem_stream(const dcora_problem *p);
+/* Kernel launches issued by this handle since creation. */
+int64_t dcora_problem_launch_count(const dcora_problem *p);
+
+/* Graph::setNeighborStates -> constructG (src/Graph.cpp:333-340,565-577):
+ * replace the linear term.  G: r x K, or NULL for zero. */
+int dcora_problem_set_G(dcora_problem *p, const double *G);
+
+/* QuadraticProblem::f (src/QuadraticProblem.cpp:38-51): f_out[num_agents]. */
+int dcora_problem_f(dcora_problem *p, const double *X, double *f_out);
+/* QuadraticProblem::EucGrad (:53-59): EG = X*Q + G. */
+int dcora_problem_egrad(dcora_problem *p, const double *X, double *EG);
+/* QuadraticProblem::EucHessianEta (:61-68): HV = V*Q. */
+int dcora_problem_hessvec(dcora_problem *p, const double *V, double *HV);
+/* QuadraticProblem::PreConditioner (:70-84): proj_X((Q+reg I)^-1 V^T)^T. */
+int dcora_problem_precond(dcora_problem *p, const double *X, const double *V,
+                          double *OUT);
+/* QuadraticProblem::RieGrad / RieGradNorm (:86-123). */
+int dcora_problem_rgrad(dcora_problem *p, const double *X, double *RG);
+int dcora_problem_rgradnorm(dcora_problem *p, const double *X, double *norm_out);
+/* QuadraticProblem::Retract (:125-136,236-259). */
+int dcora_problem_retract(dcora_problem *p, const double *X, const double *V,
+                          double *Xout, int32_t retraction);
+/* LiftedSEManifold/LiftedRAManifold::projectToTangentSpace
+ * (src/manifold/LiftedManifold.cpp:37-41,104-108). */
+int dcora_problem_project_tangent(dcora_problem *p, const double *X,
+                                  const double *V, double *OUT);
+/* LiftedSEManifold/LiftedRAManifold::project = projectToSEMatrix /
+ * projectToRAMatrix (src/DCORA_utils.cpp:2201-2220). */
+int dcora_problem_project_manifold(dcora_problem *p, const double *M,
+                                   double *OUT);
+
+/* QuadraticOptimizer::optimize (src/QuadraticOptimizer.cpp:28-50) for every
+ * agent of the batch at once; active[a]==0 leaves agent a untouched
+ * (active==NULL: all).  results[num_agents]. */
+int dcora_rtr_solve(dcora_problem *p, const double *X0, double *Xopt,
+                    const dcora_ropt_params *params, const uint8_t *active,
+                    dcora_ropt_result *results);
+
+/* Certification of a CENTRALISED problem (num_agents == 1):
+ * constructDualCertificateMatrix{PGO,RASLAM} + fastVerification
+ * (src/DCORA_utils.cpp:1713-1735,1898-1982).  S = Q - Lambda is applied
+ * implicitly; lambda_min(S) comes from a device thick-restart Lanczos
+ * (replaces CHOLMOD's PSD test and Spectra, :1737-1896).
+ *   is_psd     : 1 iff lambda_min(S + eta I) > 0 (the reference's verdict)
+ *   lambda_min : smallest eigenvalue of S
+ *   theta      : v^T S v   (fastVerification's *theta)
+ *   v          : k doubles, reference ordering (may be NULL) */
+typedef struct {
+  int32_t is_psd;
+  int32_t converged;
+  int32_t matvecs;
+  int32_t restarts;
+  double lambda_min;
+  double theta;
+  double residual;
+} dcora_certify_result;
+int dcora_certify(dcora_problem *p, const double *X, double eta,
+                  int32_t max_matvecs, double tol, dcora_certify_result *res,
+                  double *v);
+
+/* QuadraticProblem::escapeSaddle (src/QuadraticProblem.cpp:138-234).  `p` is
+ * the rank-r problem, Xopt is (r-1) x k, X is r x k.  Returns DCORA_SOFT_FAIL
+ * when no trial point decreases the cost (the reference returns false). */
+int dcora_problem_escape_saddle(dcora_problem *p, const double *Xopt,
+                                double theta, const double *v,
+                                double gradient_tolerance,
+                                double preconditioned_gradient_tolerance,
+                                int32_t is_second_order, int32_t retraction,
+                                double *X);
+
+/* K1 in isolation, for roofline measurement: runs the Q-SpMM `iters` times on
+ * device-resident data and returns the mean kernel time (CUDA events on the
+ * handle's stream) and the algorithmic bytes of one launch
+ * (8*nnz(Q) + 16*r*K). */
+int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
+                            double *algorithmic_bytes);
+
+/* Host-only self checks of the setup code (no GPU needed, no usable result):
+ * max |Y_layout - Y_csr| of the CSR -> BSR/remainder conversion on internally
+ * generated X, and the relative residual of the host Cholesky factor of
+ * Q + reg*I on an internally generated right-hand side. */
+int dcora_selfcheck_layout(const dcora_agent_desc *agents, int32_t num_agents,
+                           int32_t r, int32_t d, int32_t order,
+                           double *max_abs_err);
+int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const int32_t *col,
+                             const double *val, int32_t dh, int32_t npose,
+                             double reg, double *rel_residual,
+                             int64_t *factor_nnz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCORA_B200_H_ */

@@ -158,6 +158,11 @@ def read_g2o(filename):
                 assert i not in gt, "duplicate pose ID"
                 gt[i] = (quat_to_rot(v[3], v[4], v[5], v[6]), np.array(v[0:3]))
             elif tok[0] == "EDGE_SE2":
+                # NB the reference only sets `dim` on VERTEX lines (:224-256)
+                # and would LOG(FATAL) at :366 on a file without them (e.g.
+                # data/kitti_00.g2o); inferring it from the edge type is a
+                # deliberate, documented deviation.
+                dim = dim or 2
                 i, j = int(tok[1]), int(tok[2])
                 dx, dy, dth, I11, I12, I13, I22, I23, I33 = map(float, tok[3:12])
                 tran = np.array([[I11, I12], [I12, I22]])
@@ -166,6 +171,7 @@ def read_g2o(filename):
                 tau.append(2.0 / np.trace(np.linalg.inv(tran)))   # :288-292
                 kap.append(I33)
             elif tok[0] == "EDGE_SE3:QUAT":
+                dim = dim or 3
                 i, j = int(tok[1]), int(tok[2])
                 v = list(map(float, tok[3:31]))
                 dx, dy, dz, qx, qy, qz, qw = v[0:7]

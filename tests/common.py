@@ -1,0 +1,73 @@
+"""Shared helpers of the test-suite: golden fixture loading, oracle problems,
+and the GPU problem built through the C-ABI from the same Q."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle import dataio, graph, manifold as mf, solver
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name, prefix=""):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = int(z["d"])
+
+    def get(grp, key):
+        return z[f"{prefix}{grp}_{key}"]
+    pp = dataio.PosePose(d, get("pp", "r1"), get("pp", "p1"), get("pp", "r2"),
+                         get("pp", "p2"), get("pp", "R"), get("pp", "t"),
+                         get("pp", "kappa"), get("pp", "tau"), get("pp", "weight"))
+    pl = dataio.PoseLandmark(d, get("pl", "r1"), get("pl", "p1"), get("pl", "r2"),
+                             get("pl", "p2"), get("pl", "t"), get("pl", "tau"),
+                             get("pl", "weight"))
+    rg = dataio.Range(get("rg", "r1"), get("rg", "p1"), get("rg", "r2"), get("rg", "p2"),
+                      get("rg", "type1"), get("rg", "type2"), get("rg", "l"),
+                      get("rg", "range"), get("rg", "precision"), get("rg", "weight"))
+    meas = dataio.Measurements(d, pp, pl, rg)
+    info = dict(kind=str(z["kind"]), n=int(z["n"]), l=int(z["l"]), b=int(z["b"]),
+                has_gt=bool(z["has_gt"]), X_gt=z["X_gt"], d=d)
+    return meas, info
+
+
+def central_problem(name, r, use_precond=True):
+    """Oracle problem + Graph of the centralised problem of a golden dataset."""
+    meas, info = load_golden(name)
+    ra = info["kind"] == "pyfg"
+    g = graph.Graph(0, r, info["d"], ra=ra).set_measurements(meas)
+    Q = g.quadratic_matrix()
+    L = mf.Layout(r, info["d"], g.n, g.l, g.b, ra=ra)
+    reg = graph.precond_regularization(Q, ra)
+    P = solver.QuadraticProblem(L, Q, precond_reg=reg, use_precond=use_precond)
+    return P, g, info
+
+
+def gpu_problem(P, precond=True, device=0):
+    """dcora_b200.QuadraticProblem from an oracle problem's Q (through the C-ABI)."""
+    import dcora_b200 as dc
+    L = P.L
+    ag = dc.AgentData(n=L.n, l=L.l, b=L.b, Q=P.Q,
+                      G=P.G if np.any(P.G) else None,
+                      precond_reg=P.reg if precond else None)
+    return dc.QuadraticProblem(ag, L.r, L.d, dc.ORDER_RA if L.ra else dc.ORDER_SE, device)
+
+
+def split_contiguous(meas, n, num_robots):
+    """The partition rule of examples/MultiRobotExample.cpp:56-118: contiguous
+    ranges of n/num_robots poses per robot, the last robot takes the rest."""
+    per = n // num_robots
+    rob = np.minimum(np.arange(n) // per, num_robots - 1)
+    start = np.arange(num_robots) * per
+    pp = meas.pp
+    r1, r2 = rob[pp.p1], rob[pp.p2]
+    out = dataio.PosePose(meas.d, r1, pp.p1 - start[r1], r2, pp.p2 - start[r2],
+                          pp.R, pp.t, pp.kappa, pp.tau, pp.weight)
+    counts = np.bincount(rob, minlength=num_robots)
+    return dataio.Measurements(meas.d, pp=out), counts, start
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
