@@ -93,6 +93,11 @@ class _Arg:
         if self.torch:
             assert x.is_cuda and x.is_contiguous() and tuple(x.shape) == (K, r), \
                 "CUDA tensors must be contiguous with shape (K, r)"
+            if not out:
+                # the handle launches on its own stream: the producer of a
+                # device-resident input must have finished
+                import torch
+                torch.cuda.current_stream(x.device).synchronize()
             self.buf = x
             self.ptr = C.c_void_p(x.data_ptr())
         else:

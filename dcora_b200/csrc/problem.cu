@@ -76,7 +76,9 @@ int export_matrix(dcora_problem *p, const double *src, double *dst, int r) {
     DCORA_TRY(launch_permute(p, src, p->stage, r, false));
     DCORA_CUDA(cudaMemcpyAsync(dst, p->stage, bytes, cudaMemcpyDeviceToHost, p->stream));
   }
-  if (!dev) DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  // The C-ABI is synchronous: results are complete when a call returns, also
+  // for device destinations (the caller's stream is not ours).
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
   return DCORA_OK;
 }
 
