@@ -36,6 +36,10 @@ class ROptResult(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class HaloSegment(C.Structure):
+    _fields_ = [("n", C.c_int32), ("l", C.c_int32), ("b", C.c_int32)]
+
+
 class CertifyResult(C.Structure):
     _fields_ = [("is_psd", C.c_int32), ("converged", C.c_int32),
                 ("matvecs", C.c_int32), ("restarts", C.c_int32),
@@ -59,6 +63,7 @@ SYMBOLS = {
     "dcora_problem_num_agents": (C.c_int32, [VP]),
     "dcora_problem_nnz": (C.c_int64, [VP]),
     "dcora_problem_factor_nnz": (C.c_int64, [VP]),
+    "dcora_problem_precond_reg": (C.c_double, [VP, C.c_int32]),
     "dcora_problem_stream": (VP, [VP]),
     "dcora_problem_launch_count": (C.c_int64, [VP]),
     "dcora_problem_set_G": (C.c_int, [VP, VP]),
@@ -77,6 +82,14 @@ SYMBOLS = {
                                 C.POINTER(CertifyResult), VP]),
     "dcora_problem_escape_saddle": (C.c_int, [VP, VP, C.c_double, VP, C.c_double,
                                               C.c_double, C.c_int32, C.c_int32, VP]),
+    "dcora_problem_set_coupling": (C.c_int, [VP, C.POINTER(HaloSegment), C.c_int32,
+                                             c_int32_p, c_int32_p, c_double_p]),
+    "dcora_problem_halo_dim": (C.c_int64, [VP]),
+    "dcora_problem_update_G": (C.c_int, [VP, VP, VP, c_uint8_p]),
+    "dcora_problem_pack_columns": (C.c_int, [VP, VP, c_int32_p, C.c_int64, VP]),
+    "dcora_problem_cost_terms": (C.c_int, [VP, VP, c_double_p, c_double_p]),
+    "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
+                                                c_uint8_p, VP]),
     "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
     "dcora_selfcheck_layout": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, c_double_p]),

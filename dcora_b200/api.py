@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import AgentDesc, CertifyResult, ROptParams, ROptResult, check
+from ._lib import AgentDesc, CertifyResult, HaloSegment, ROptParams, ROptResult, check
 
 ORDER_SE, ORDER_RA = 0, 1
 RETRACT_QF, RETRACT_POLAR = 0, 1
@@ -36,7 +36,7 @@ class AgentData:
     l: int = 0
     b: int = 0
     G: np.ndarray | None = None
-    precond_reg: float | None = 0.1
+    precond_reg: float | str | None = 0.1   # None: no factor; "auto_ra": RA rule
 
 
 @dataclass
@@ -128,6 +128,7 @@ class QuadraticProblem:
             self.A = _parent.A
             self.K = _parent.K
             self.koff = _parent.koff
+            self.KH = getattr(_parent, "KH", 0)
             return
         if isinstance(agents, AgentData):
             agents = [agents]
@@ -157,10 +158,12 @@ class QuadraticProblem:
                 assert G.shape == (r, k)
                 keep.append(G)
                 descs[i].G = G.ctypes.data_as(_lib.c_double_p)
-            descs[i].precond_reg = -1.0 if ag.precond_reg is None else ag.precond_reg
+            descs[i].precond_reg = (-1.0 if ag.precond_reg is None else
+                                    -2.0 if ag.precond_reg == "auto_ra" else ag.precond_reg)
             koff.append(koff[-1] + k)
         self.koff = koff
         self.K = koff[-1]
+        self.KH = 0
         h = C.c_void_p()
         check(self.lib.dcora_problem_create(descs, self.A, r, d, order, device,
                                             C.byref(h)))
@@ -195,6 +198,9 @@ class QuadraticProblem:
 
     def factor_nnz(self):
         return self.lib.dcora_problem_factor_nnz(self.h)
+
+    def precond_reg(self, agent=0):
+        return self.lib.dcora_problem_precond_reg(self.h, agent)
 
     def launch_count(self):
         return self.lib.dcora_problem_launch_count(self.h)
@@ -284,6 +290,68 @@ class QuadraticProblem:
             self.h, a.ptr, float(eta), int(max_matvecs), float(tol), C.byref(res),
             v.ctypes.data_as(C.c_void_p) if v is not None else None))
         return res, v
+
+    # -- multi-agent RBCD (Agent.cpp:113-152,844-906,1202-1278; Graph.cpp:685-822)
+    def set_coupling(self, C, halo_segments=()):
+        """Register the cross-agent coupling: C is a scipy CSR (or (rowptr, col,
+        val)) of shape (K + KH, K); halo_segments = [(n, l, b), ...]."""
+        if isinstance(C, tuple):
+            rowptr, col, val = C
+        else:
+            C = C.tocsr()
+            rowptr, col, val = C.indptr, C.indices, C.data
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        segs = (HaloSegment * max(1, len(halo_segments)))()
+        KH = 0
+        for i, (n, l, b) in enumerate(halo_segments):
+            segs[i].n, segs[i].l, segs[i].b = n, l, b
+            KH += (self.d + 1) * n + l + b
+        assert len(rowptr) == self.K + KH + 1, "coupling has the wrong number of rows"
+        check(self.lib.dcora_problem_set_coupling(
+            self.h, segs, len(halo_segments), rowptr.ctypes.data_as(_lib.c_int32_p),
+            col.ctypes.data_as(_lib.c_int32_p), val.ctypes.data_as(_lib.c_double_p)))
+        self.KH = KH
+
+    def _mask(self, active):
+        if active is None:
+            return None, None
+        arr = np.ascontiguousarray(active, dtype=np.uint8)
+        assert arr.shape == (self.A,)
+        return arr, arr.ctypes.data_as(_lib.c_uint8_p)
+
+    def update_G(self, X, H=None, active=None):
+        a = _Arg(X, self.r, self.K)
+        h = _Arg(H, self.r, self.KH) if (H is not None and self.KH > 0) else None
+        keep, act = self._mask(active)
+        check(self.lib.dcora_problem_update_G(self.h, a.ptr, h.ptr if h else None, act))
+
+    def pack_columns(self, X, idx, out=None):
+        a = _Arg(X, self.r, self.K)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        if out is None:
+            out = _new_out(X, self.r, len(idx))
+        o = _Arg(out, self.r, len(idx), out=True)
+        check(self.lib.dcora_problem_pack_columns(
+            self.h, a.ptr, idx.ctypes.data_as(_lib.c_int32_p), len(idx), o.ptr))
+        return out
+
+    def cost_terms(self, X):
+        a = _Arg(X, self.r, self.K)
+        q = (C.c_double * self.A)()
+        l = (C.c_double * self.A)()
+        check(self.lib.dcora_problem_cost_terms(self.h, a.ptr, q, l))
+        return np.array(q[:]), np.array(l[:])
+
+    def combine_project(self, a, A, b, B, active=None):
+        x, y = _Arg(A, self.r, self.K), _Arg(B, self.r, self.K)
+        out = _new_out(A, self.r, self.K)
+        o = _Arg(out, self.r, self.K, out=True)
+        keep, act = self._mask(active)
+        check(self.lib.dcora_problem_combine_project(self.h, float(a), x.ptr, float(b),
+                                                     y.ptr, act, o.ptr))
+        return out
 
     def time_spmm(self, iters=20):
         ms, by = C.c_double(), C.c_double()

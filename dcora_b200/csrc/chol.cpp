@@ -232,4 +232,97 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
   return DCORA_OK;
 }
 
+
+// Largest eigenvalue of a symmetric CSR matrix by Lanczos with full
+// re-orthogonalisation (host, set-up only).  Replaces the Spectra
+// SymEigsSolver(nev=1, ncv=6, tol=1e-3) call of
+// Graph::computePreconditionerRegularization (src/Graph.cpp:1919-1960).
+// Returns < 0 when it does not converge (caller falls back to 0.1 like the
+// reference).
+double lambda_max_lanczos(int k, const int *Ap, const int *Ai, const double *Ax,
+                          double tol, int max_steps) {
+  if (k <= 0) return -1.0;
+  const int m = std::min(max_steps, k);
+  std::vector<std::vector<double>> V;
+  V.reserve(m + 1);
+  std::vector<double> alpha, beta, w(k);
+  uint64_t st = 0x2545F4914F6CDD1Dull;
+  std::vector<double> v(k);
+  double nrm = 0.0;
+  for (int i = 0; i < k; ++i) {
+    st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+    v[i] = (double)(st >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    nrm += v[i] * v[i];
+  }
+  nrm = 1.0 / std::sqrt(nrm);
+  for (double &x : v) x *= nrm;
+  V.push_back(v);
+  double theta = -1.0;
+  for (int j = 0; j < m; ++j) {
+    const std::vector<double> &vj = V[j];
+    for (int i = 0; i < k; ++i) {
+      double s = 0.0;
+      for (int p = Ap[i]; p < Ap[i + 1]; ++p) s += Ax[p] * vj[Ai[p]];
+      w[i] = s;
+    }
+    double a = 0.0;
+    for (int i = 0; i < k; ++i) a += w[i] * vj[i];
+    alpha.push_back(a);
+    for (int pass = 0; pass < 2; ++pass)
+      for (int c = 0; c <= j; ++c) {
+        double h = 0.0;
+        for (int i = 0; i < k; ++i) h += V[c][i] * w[i];
+        for (int i = 0; i < k; ++i) w[i] -= h * V[c][i];
+      }
+    double b = 0.0;
+    for (int i = 0; i < k; ++i) b += w[i] * w[i];
+    b = std::sqrt(b);
+    // largest Ritz value of the (j+1) x (j+1) tridiagonal by bisection-free
+    // power of QL is overkill: use Sturm bisection on the Gershgorin interval
+    const int q = j + 1;
+    double lo = alpha[0], hi = alpha[0];
+    for (int i = 0; i < q; ++i) {
+      const double rad = (i > 0 ? std::fabs(beta[i - 1]) : 0.0) +
+                         (i + 1 < q ? std::fabs(beta[i]) : 0.0);
+      lo = std::min(lo, alpha[i] - rad);
+      hi = std::max(hi, alpha[i] + rad);
+    }
+    auto count_below = [&](double x) {  // number of eigenvalues < x
+      int cnt = 0;
+      double dprev = 1.0;
+      for (int i = 0; i < q; ++i) {
+        const double b2 = i > 0 ? beta[i - 1] * beta[i - 1] : 0.0;
+        double dcur = alpha[i] - x - (i > 0 ? b2 / dprev : 0.0);
+        if (dcur == 0.0) dcur = -1e-300;
+        if (dcur < 0.0) ++cnt;
+        dprev = dcur;
+      }
+      return cnt;
+    };
+    double a0 = lo, b0 = hi;
+    for (int it = 0; it < 200 && b0 - a0 > 1e-14 * std::max(1.0, std::fabs(b0)); ++it) {
+      const double mid = 0.5 * (a0 + b0);
+      if (count_below(mid) >= q) b0 = mid; else a0 = mid;
+    }
+    theta = 0.5 * (a0 + b0);
+    // residual of the top Ritz pair = |b * s_q|, s = eigenvector of T: solve by
+    // the three-term recurrence (T - theta I) s = 0 from the top
+    std::vector<double> sv(q);
+    sv[0] = 1.0;
+    if (q > 1) sv[1] = -(alpha[0] - theta) / beta[0];
+    for (int i = 1; i + 1 < q; ++i)
+      sv[i + 1] = -((alpha[i] - theta) * sv[i] + beta[i - 1] * sv[i - 1]) / beta[i];
+    double sn = 0.0;
+    for (double x : sv) sn += x * x;
+    const double res = std::fabs(b * sv[q - 1]) / std::sqrt(sn);
+    if (res <= tol * std::fabs(theta) || b <= 1e-300) return theta;
+    if (j + 1 == m) break;
+    beta.push_back(b);
+    std::vector<double> vn(k);
+    for (int i = 0; i < k; ++i) vn[i] = w[i] / b;
+    V.push_back(std::move(vn));
+  }
+  return k <= max_steps ? theta : -1.0;
+}
+
 }  // namespace dcora

@@ -72,6 +72,37 @@ struct HostLayout {
 int build_layout(const dcora_agent_desc *agents, int A, int r, int d, int order,
                  HostLayout *out);
 
+// Host-side converted coupling matrix (layout.cpp: build_coupling_layout).
+struct HostCoupling {
+  int64_t KH = 0;              // halo columns
+  bool identity_perm = true;
+  std::vector<int> perm_h;     // internal halo col -> reference halo col
+  std::vector<int> browptr, bcol, prowcol;
+  std::vector<double> bval;
+  std::vector<int> rem_row, rem_rowptr, rem_col;
+  std::vector<uint8_t> rem_assign;
+  std::vector<double> rem_val;
+};
+int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
+                          const std::vector<int> &n, const std::vector<int> &l,
+                          const std::vector<int> &poff, const dcora_halo_segment *segs,
+                          int nseg, const int64_t *rowptr, const int32_t *col,
+                          const double *val, HostCoupling *out);
+
+// Device copy of the coupling (rbcd.cu).
+struct DeviceCoupling {
+  int device = 0;
+  int64_t KH = 0, nnzb = 0, nrem_rows = 0, nnz_in = 0;
+  bool identity_perm = true;
+  int *perm_h = nullptr;
+  int *browptr = nullptr, *bcol = nullptr;
+  double *bval = nullptr;
+  int *rem_row = nullptr, *rem_rowptr = nullptr, *rem_col = nullptr, *rem_agent = nullptr;
+  uint8_t *rem_assign = nullptr;
+  double *rem_val = nullptr;
+  ~DeviceCoupling();
+};
+
 // Host sparse Cholesky factor of one agent (chol.cpp), internal ordering.
 struct HostFactor {
   int k = 0;
@@ -84,6 +115,9 @@ struct HostFactor {
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
                     const std::vector<double> &Ax, int dh, int npose,
                     HostFactor *out);
+
+double lambda_max_lanczos(int k, const int *Ap, const int *Ai, const double *Ax,
+                          double tol, int max_steps);
 
 // Device-side factor for the whole batch (sptrsv.cu).
 struct DeviceFactor {
@@ -112,6 +146,7 @@ struct DeviceMatrices {
   int nchunks = 0;
   std::vector<int64_t> coff;
   std::vector<int> n, l, b, poff, agent_chunk0_h;
+  std::vector<double> reg;  // per agent: regularisation of the factor (<0: none)
   bool identity_perm = true;
   int *perm = nullptr;
   int *browptr = nullptr, *bcol = nullptr, *prowcol = nullptr;
@@ -133,6 +168,11 @@ struct DeviceMatrices {
 struct dcora_problem {
   int r = 0;
   std::shared_ptr<dcora::DeviceMatrices> M;
+  std::shared_ptr<dcora::DeviceCoupling> C;  // cross-agent coupling (RBCD), optional
+  double *xe = nullptr;            // [X | H] extended vector, r*(K+KH)
+  double *hstage = nullptr;        // halo staging (reference layout)
+  int *pack_idx = nullptr;         // cached public-column index list (device)
+  std::vector<int32_t> pack_idx_host;
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
   int64_t launches = 0;

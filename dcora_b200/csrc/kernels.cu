@@ -520,30 +520,42 @@ reduce_scalars_kernel(const int *__restrict__ agent_chunk0,
 }  // namespace
 
 // ------------------------------------------------------------- dispatchers
-int launch_spmm(dcora_problem *p, const double *X, const double *G, double *Y,
-                int mask_flag) {
+int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
+                    const double *G, double *Y, int mask_flag) {
   DeviceMatrices &M = *p->M;
-  if (M.np > 0) {
+  if (A.np > 0) {
     DCORA_DISPATCH_RD(p->r, M.d, {
       constexpr int PPW = Map<DH>::PPW;
       const int ppc = 4 * PPW;
-      const int grid = (M.np + ppc - 1) / ppc;
+      const int grid = (A.np + ppc - 1) / ppc;
       bsr_spmm_kernel<R, DH><<<grid, 128, 0, p->stream>>>(
-          M.np, M.browptr, M.bcol, M.bval, M.prowcol, M.pose_agent, p->flags,
+          A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
           mask_flag, X, G, Y);
     })
     DCORA_LAUNCH_CHECK(p);
   }
-  if (M.nrem_rows > 0) {
+  if (A.nrem_rows > 0) {
     DCORA_DISPATCH_R(p->r, {
-      const int grid = (int)((M.nrem_rows + 127) / 128);
+      const int grid = (int)((A.nrem_rows + 127) / 128);
       rem_spmm_kernel<R><<<grid, 128, 0, p->stream>>>(
-          (int)M.nrem_rows, M.rem_row, M.rem_rowptr, M.rem_col, M.rem_val,
-          M.rem_assign, M.rem_agent, p->flags, mask_flag, X, G, Y);
+          (int)A.nrem_rows, A.rem_row, A.rem_rowptr, A.rem_col, A.rem_val,
+          A.rem_assign, A.rem_agent, p->flags, mask_flag, X, G, Y);
     })
     DCORA_LAUNCH_CHECK(p);
   }
   return DCORA_OK;
+}
+
+int launch_spmm(dcora_problem *p, const double *X, const double *G, double *Y,
+                int mask_flag) {
+  DeviceMatrices &M = *p->M;
+  SpmmMat A;
+  A.np = M.np; A.browptr = M.browptr; A.bcol = M.bcol; A.bval = M.bval;
+  A.prowcol = M.prowcol; A.pose_agent = M.pose_agent;
+  A.nrem_rows = M.nrem_rows; A.rem_row = M.rem_row; A.rem_rowptr = M.rem_rowptr;
+  A.rem_col = M.rem_col; A.rem_val = M.rem_val; A.rem_assign = M.rem_assign;
+  A.rem_agent = M.rem_agent;
+  return launch_spmm_mat(p, A, X, G, Y, mask_flag);
 }
 
 template <int OP>
@@ -615,15 +627,20 @@ int launch_copy(dcora_problem *p, double *out, const double *x, int mask_flag) {
   return launch_axpby(p, out, -1, 1.0, x, -1, 0.0, nullptr, mask_flag);
 }
 
-int launch_permute(dcora_problem *p, const double *in, double *out, int r,
-                   bool to_internal) {
-  DeviceMatrices &M = *p->M;
-  const int64_t tot = M.K * r;
+int launch_permute_cols(dcora_problem *p, const int *perm, int64_t ncols,
+                        const double *in, double *out, int r, bool to_internal) {
+  const int64_t tot = ncols * r;
+  if (tot == 0) return DCORA_OK;
   const int grid = (int)((tot + 255) / 256);
-  permute_kernel<<<grid, 256, 0, p->stream>>>(M.K, r, M.perm, in, out,
+  permute_kernel<<<grid, 256, 0, p->stream>>>(ncols, r, perm, in, out,
                                               to_internal ? 1 : 0);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
+}
+
+int launch_permute(dcora_problem *p, const double *in, double *out, int r,
+                   bool to_internal) {
+  return launch_permute_cols(p, p->M->perm, p->M->K, in, out, r, to_internal);
 }
 
 int launch_reduce_scalars(dcora_problem *p, int nslots, const int *dst_slots) {

@@ -25,6 +25,19 @@ enum Flag : int {
   NF
 };
 
+// A block-sparse operand of the SpMM kernels: BSR over output pose blocks +
+// scalar CSR remainder (see layout.cpp).
+struct SpmmMat {
+  int np = 0;
+  const int *browptr = nullptr, *bcol = nullptr, *prowcol = nullptr, *pose_agent = nullptr;
+  const double *bval = nullptr;
+  int64_t nrem_rows = 0;
+  const int *rem_row = nullptr, *rem_rowptr = nullptr, *rem_col = nullptr, *rem_agent = nullptr;
+  const uint8_t *rem_assign = nullptr;
+  const double *rem_val = nullptr;
+};
+int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
+                    const double *G, double *Y, int mask_flag);
 // Y = X*Q (+G).  mask_flag < 0: all agents.
 int launch_spmm(dcora_problem *p, const double *X, const double *G, double *Y,
                 int mask_flag);
@@ -55,7 +68,8 @@ int launch_copy(dcora_problem *p, double *out, const double *x, int mask_flag);
 // layout permutation between reference and internal column order
 int launch_permute(dcora_problem *p, const double *in, double *out, int r,
                    bool to_internal);
-// lift rank: out (r x K) <- [in ((r-1) x K); 0]  or out row r-1 <- v
+int launch_permute_cols(dcora_problem *p, const int *perm, int64_t ncols,
+                        const double *in, double *out, int r, bool to_internal);
 int launch_reduce_scalars(dcora_problem *p, int nslots, const int *dst_slots);
 
 // preconditioner application z = proj_X( (Q+reg I)^-1 v ) (sptrsv.cu)

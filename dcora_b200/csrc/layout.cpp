@@ -225,4 +225,134 @@ int build_layout(const dcora_agent_desc *agents, int A, int r, int d, int order,
   return DCORA_OK;
 }
 
+
+// ---------------------------------------------------------------- coupling
+// Cross-agent coupling matrix C ((K + KH) x K, CSR): G = [X | H] * C restates
+// Graph::constructLinearCostTerm{PGO,RASLAM} (Graph.cpp:685-822,1190-1772) as
+// one sparse product -- every shared edge contributes Xc * (cross block of the
+// global Q).  Rows are "extended reference" columns: the K local columns
+// (agents concatenated, each in the reference ordering) followed by the halo
+// segments (neighbour public states received from other processes), each
+// segment a pseudo-agent (n, l, b) in the same ordering.
+int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
+                          const std::vector<int> &n, const std::vector<int> &l,
+                          const std::vector<int> &poff, const dcora_halo_segment *segs,
+                          int nseg, const int64_t *rowptr, const int32_t *col,
+                          const double *val, HostCoupling *out) {
+  HostCoupling &C = *out;
+  const int dh = d + 1;
+  const int A = (int)n.size();
+  const int64_t K = coff[A];
+  std::vector<int64_t> hoff(nseg + 1, 0);
+  for (int s = 0; s < nseg; ++s) {
+    if (segs[s].n < 0 || segs[s].l < 0 || segs[s].b < 0) {
+      set_error("build_coupling_layout: bad halo segment");
+      return DCORA_ERR_ARG;
+    }
+    if (order == DCORA_ORDER_SE && (segs[s].l || segs[s].b)) {
+      set_error("build_coupling_layout: SE ordering cannot carry spheres / landmarks");
+      return DCORA_ERR_ARG;
+    }
+    hoff[s + 1] = hoff[s] + (int64_t)dh * segs[s].n + segs[s].l + segs[s].b;
+  }
+  C.KH = hoff[nseg];
+  const int64_t KE = K + C.KH;
+  if (KE >= ((int64_t)1 << 31)) {
+    set_error("build_coupling_layout: K + KH exceeds int32");
+    return DCORA_ERR_ARG;
+  }
+  // extended reference column -> extended internal column; pose-block start
+  std::vector<int> r2i(KE), blk(KE, -1);
+  for (int a = 0; a < A; ++a) {
+    const int c0 = (int)coff[a], k = (int)(coff[a + 1] - coff[a]);
+    for (int c = 0; c < k; ++c) r2i[c0 + c] = c0 + ref_to_internal(c, d, n[a], l[a], order);
+    for (int i = 0; i < n[a]; ++i)
+      for (int q = 0; q < dh; ++q) blk[c0 + i * dh + q] = c0 + i * dh;
+  }
+  C.identity_perm = (order == DCORA_ORDER_SE);
+  C.perm_h.resize(C.KH);
+  for (int s = 0; s < nseg; ++s) {
+    const int c0 = (int)(K + hoff[s]), k = (int)(hoff[s + 1] - hoff[s]);
+    for (int c = 0; c < k; ++c) {
+      const int ci = ref_to_internal(c, d, segs[s].n, segs[s].l, order);
+      r2i[c0 + c] = c0 + ci;
+      C.perm_h[hoff[s] + ci] = (int)hoff[s] + c;
+    }
+    for (int i = 0; i < segs[s].n; ++i)
+      for (int q = 0; q < dh; ++q) blk[c0 + i * dh + q] = c0 + i * dh;
+  }
+  // local internal column -> output pose block index
+  const int np = poff[A];
+  std::vector<int> oblk(K, -1);
+  for (int a = 0; a < A; ++a)
+    for (int i = 0; i < n[a]; ++i)
+      for (int q = 0; q < dh; ++q) oblk[coff[a] + i * dh + q] = poff[a] + i;
+  C.prowcol.resize(np);
+  for (int a = 0; a < A; ++a)
+    for (int i = 0; i < n[a]; ++i) C.prowcol[poff[a] + i] = (int)coff[a] + i * dh;
+
+  std::vector<std::vector<int>> cols(np);
+  std::vector<int> rem_count(K, 0);
+  for (int64_t R = 0; R < KE; ++R) {
+    const int ri = r2i[R];
+    for (int64_t p = rowptr[R]; p < rowptr[R + 1]; ++p) {
+      if (col[p] < 0 || col[p] >= K) {
+        set_error("build_coupling_layout: column index out of range");
+        return DCORA_ERR_ARG;
+      }
+      const int ci = r2i[col[p]];
+      if (blk[ri] >= 0 && oblk[ci] >= 0) {
+        std::vector<int> &v = cols[oblk[ci]];
+        if (std::find(v.begin(), v.end(), blk[ri]) == v.end()) v.push_back(blk[ri]);
+      } else {
+        rem_count[ci]++;
+      }
+    }
+  }
+  C.browptr.assign(np + 1, 0);
+  for (int i = 0; i < np; ++i) {
+    std::sort(cols[i].begin(), cols[i].end());
+    C.browptr[i + 1] = C.browptr[i] + (int)cols[i].size();
+  }
+  C.bcol.resize(C.browptr[np]);
+  for (int i = 0; i < np; ++i)
+    std::copy(cols[i].begin(), cols[i].end(), C.bcol.begin() + C.browptr[i]);
+  std::vector<std::vector<int>>().swap(cols);
+  C.bval.assign((size_t)C.bcol.size() * dh * dh, 0.0);
+  std::vector<int> slot(K, -1);
+  C.rem_rowptr.assign(1, 0);
+  for (int ci = 0; ci < K; ++ci) {
+    const bool extra = oblk[ci] < 0;
+    if (extra || rem_count[ci] > 0) {
+      slot[ci] = (int)C.rem_row.size();
+      C.rem_row.push_back(ci);
+      C.rem_assign.push_back(extra ? 1 : 0);
+      C.rem_rowptr.push_back(C.rem_rowptr.back() + rem_count[ci]);
+    }
+  }
+  C.rem_col.assign(C.rem_rowptr.back(), 0);
+  C.rem_val.assign(C.rem_rowptr.back(), 0.0);
+  std::vector<int> fill(C.rem_rowptr.begin(), C.rem_rowptr.end() - 1);
+  for (int64_t R = 0; R < KE; ++R) {
+    const int ri = r2i[R];
+    for (int64_t p = rowptr[R]; p < rowptr[R + 1]; ++p) {
+      const int ci = r2i[col[p]];
+      if (blk[ri] >= 0 && oblk[ci] >= 0) {
+        const int i = oblk[ci];
+        const int *b0 = C.bcol.data() + C.browptr[i];
+        const int *b1 = C.bcol.data() + C.browptr[i + 1];
+        const int64_t q = std::lower_bound(b0, b1, blk[ri]) - C.bcol.data();
+        // component of the output column / source column inside its block
+        const int a_out = ci - C.prowcol[i], b_src = ri - blk[ri];
+        C.bval[(size_t)q * dh * dh + a_out * dh + b_src] += val[p];
+      } else {
+        const int w = fill[slot[ci]]++;
+        C.rem_col[w] = ri;
+        C.rem_val[w] = val[p];
+      }
+    }
+  }
+  return DCORA_OK;
+}
+
 }  // namespace dcora

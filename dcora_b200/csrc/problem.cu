@@ -132,7 +132,7 @@ double *dcora_problem::vec(int i) {
 dcora_problem::~dcora_problem() {
   if (M) cudaSetDevice(M->device);
   for (double *w : ws) cudaFree(w);
-  cudaFree(G); cudaFree(stage); cudaFree(partials); cudaFree(scal); cudaFree(flags);
+  cudaFree(G); cudaFree(stage); cudaFree(xe); cudaFree(hstage); cudaFree(pack_idx); cudaFree(partials); cudaFree(scal); cudaFree(flags);
   cudaFreeHost(h_scal); cudaFreeHost(h_flags);
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
@@ -216,7 +216,9 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
 
   // ---- preconditioner factors (host) -> device
   bool any = false;
-  for (int a = 0; a < num_agents; ++a) any = any || agents[a].precond_reg >= 0.0;
+  for (int a = 0; a < num_agents; ++a)
+    any = any || agents[a].precond_reg >= 0.0 || agents[a].precond_reg == DCORA_REG_AUTO_RA;
+  M->reg.assign(num_agents, -1.0);
   if (any) {
     std::vector<HostFactor> HF(num_agents);
     std::vector<int> rcs(num_agents, DCORA_OK);
@@ -235,7 +237,12 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       for (int i = 0; i < k; ++i) Ap[i + 1] += Ap[i];
       std::vector<int> Ai(Ap[k]);
       std::vector<double> Ax(Ap[k]);
-      const double reg = g.precond_reg >= 0.0 ? g.precond_reg : 0.0;
+      double reg = g.precond_reg >= 0.0 ? g.precond_reg : 0.0;
+      if (g.precond_reg == DCORA_REG_AUTO_RA) {
+        const double lm = lambda_max_lanczos(k, g.rowptr, g.col, g.val, 1e-3, 300);
+        reg = lm > 0.0 ? lm / (1e6 - 1.0) : 0.1;
+      }
+      M->reg[a] = reg;
       for (int R = 0; R < k; ++R) {
         const int ri = ref2int[R];
         int w = Ap[ri];
@@ -290,6 +297,7 @@ int dcora_problem_clone_rank(const dcora_problem *src, int32_t r, dcora_problem 
   dcora_problem *p = new dcora_problem();
   p->r = r;
   p->M = src->M;
+  p->C = src->C;
   int rc = alloc_handle_buffers(p);
   if (rc != DCORA_OK) { delete p; return rc; }
   *out = p;
@@ -303,6 +311,10 @@ int32_t dcora_problem_rank(const dcora_problem *p) { return p ? p->r : 0; }
 int32_t dcora_problem_num_agents(const dcora_problem *p) { return p ? p->M->A : 0; }
 int64_t dcora_problem_nnz(const dcora_problem *p) { return p ? p->M->nnz_in : 0; }
 int64_t dcora_problem_factor_nnz(const dcora_problem *p) { return p ? p->M->F.nnzL : 0; }
+double dcora_problem_precond_reg(const dcora_problem *p, int32_t agent) {
+  if (!p || agent < 0 || agent >= (int)p->M->reg.size()) return -1.0;
+  return p->M->reg[agent];
+}
 void *dcora_problem_stream(const dcora_problem *p) { return p ? (void *)p->stream : nullptr; }
 int64_t dcora_problem_launch_count(const dcora_problem *p) { return p ? p->launches : 0; }
 

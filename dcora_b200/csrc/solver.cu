@@ -287,7 +287,7 @@ static int gradient_at(dcora_problem *p, const double *x1, double *EG, double *g
   return launch_dots(p, 1, xs, xs, mask);
 }
 
-static int set_user_mask(dcora_problem *p, const uint8_t *active) {
+int set_user_mask(dcora_problem *p, const uint8_t *active) {
   const int A = p->M->A;
   DCORA_CUDA(cudaMemcpyAsync(p->h_flags, p->flags, sizeof(int) * NF * A,
                              cudaMemcpyDeviceToHost, p->stream));

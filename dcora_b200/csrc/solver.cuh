@@ -15,4 +15,7 @@ int launch_combine_f(dcora_problem *p, int slot, int with_G, int mask_flag);
 // f(X) per agent into scal slot; tmp receives X*Q
 int eval_f(dcora_problem *p, const double *X, double *tmp, int slot, int mask_flag);
 
+// flags[a][F_USER] <- active[a] (NULL: all agents)
+int set_user_mask(dcora_problem *p, const uint8_t *active);
+
 }  // namespace dcora

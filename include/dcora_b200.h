@@ -46,6 +46,9 @@ extern "C" {
 #define DCORA_ORDER_SE 0
 #define DCORA_ORDER_RA 1
 
+#define DCORA_REG_NONE (-1.0)
+#define DCORA_REG_AUTO_RA (-2.0)
+
 #define DCORA_RETRACT_QF 0    /* ROPTLIB Stiefel qf retraction, diag(R)>0 */
 #define DCORA_RETRACT_POLAR 1 /* polar factor (projectToStiefelManifold)  */
 
@@ -69,7 +72,10 @@ typedef struct {
   const int32_t *col;     /* nnz                                                */
   const double *val;      /* nnz                                                */
   const double *G;        /* r x k column-major, or NULL for G = 0              */
-  double precond_reg;     /* reg in chol(Q + reg*I); <0 disables the factor     */
+  double precond_reg;     /* reg in chol(Q + reg*I); DCORA_REG_NONE disables the
+                             factor; DCORA_REG_AUTO_RA applies the range-aided
+                             rule lambda_max(Q)/(1e6-1), fallback 0.1
+                             (src/Graph.cpp:1919-1960)                          */
 } dcora_agent_desc;
 
 /* ROptParameters (include/DCORA/DCORA_types.h:152-200) + the hard-coded
@@ -126,6 +132,9 @@ int32_t dcora_problem_rank(const dcora_problem *p);
 int32_t dcora_problem_num_agents(const dcora_problem *p);
 int64_t dcora_problem_nnz(const dcora_problem *p);      /* nnz(Q) as given   */
 int64_t dcora_problem_factor_nnz(const dcora_problem *p);
+/* Regularisation actually used for agent a's factor (resolves
+ * DCORA_REG_AUTO_RA); < 0 when the agent has no factor. */
+double dcora_problem_precond_reg(const dcora_problem *p, int32_t agent);
 /* cudaStream_t the handle launches on (for CUDA-event timing by callers). */
 void *dcora_problem_stream(const dcora_problem *p);
 /* Kernel launches issued by this handle since creation. */
@@ -197,6 +206,54 @@ int dcora_problem_escape_saddle(dcora_problem *p, const double *Xopt,
                                 double preconditioned_gradient_tolerance,
                                 int32_t is_second_order, int32_t retraction,
                                 double *X);
+
+/* ---- multi-agent RBCD (Agent::iterate / updateX, src/Agent.cpp:535-596,
+ * 1216-1278; driver loop examples/MultiRobotExample.cpp:223-307) ---------- */
+
+/* One block of neighbour public states received from another process: a
+ * pseudo-agent of n poses, l unit spheres and b landmarks, columns in the same
+ * ordering as the agents (PoseDict / UnitSphereDict / LandmarkDict of
+ * Agent::getSharedStateDicts, src/Agent.cpp:113-152, as a packed matrix). */
+typedef struct {
+  int32_t n, l, b;
+} dcora_halo_segment;
+
+/* Register the cross-agent coupling C, a (K + KH) x K CSR matrix holding the
+ * blocks of the global data matrix that couple variables of different agents:
+ * rows are [the K columns of this handle's agents | the halo segments],
+ * columns are the K local columns.  G = [X | H] * C then equals what
+ * Graph::constructLinearCostTerm{PGO,RASLAM} (src/Graph.cpp:685-822,
+ * 1190-1772) accumulates edge by edge from the neighbour dictionaries.
+ * nseg may be 0 (all agents of the problem live in this handle). */
+int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
+                               int32_t nseg, const int32_t *rowptr,
+                               const int32_t *col, const double *val);
+int64_t dcora_problem_halo_dim(const dcora_problem *p); /* KH */
+
+/* Graph::setNeighborStates + constructG (src/Graph.cpp:333-340,565-577) for
+ * the agents with active[a] != 0 (NULL: all): G_a = ([X | H] * C)_a.
+ * X: r x K current iterates of the local agents; H: r x KH halo (may be NULL
+ * when KH == 0). */
+int dcora_problem_update_G(dcora_problem *p, const double *X, const double *H,
+                           const uint8_t *active);
+
+/* Agent::getSharedStateDicts as a gather: out[:, j] = X[:, idx[j]], idx are
+ * reference column indices into the r x K batch (host array, cached on the
+ * device on first use / when it changes). out: r x count. */
+int dcora_problem_pack_columns(dcora_problem *p, const double *X,
+                               const int32_t *idx, int64_t count, double *out);
+
+/* Per-agent 0.5 <X Q, X> and <X, G>: the global cost of the partitioned
+ * problem is sum_a quad_a + 0.5 lin_a (cross terms appear in two agents). */
+int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,
+                             double *lin_out);
+
+/* Nesterov-accelerated RBCD++ (Agent::updateY / updateV, src/Agent.cpp:
+ * 1202-1214): OUT = projectToManifold(a * A + b * B) for the active agents
+ * (others: OUT = A). */
+int dcora_problem_combine_project(dcora_problem *p, double a, const double *A,
+                                  double b, const double *B, const uint8_t *active,
+                                  double *OUT);
 
 /* K1 in isolation, for roofline measurement: runs the Q-SpMM `iters` times on
  * device-resident data and returns the mean kernel time (CUDA events on the

@@ -71,3 +71,41 @@ def split_contiguous(meas, n, num_robots):
 def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def product_measurements(meas, num_robots=None):
+    """oracle per-robot (robot id, local index) measurements -> the product's
+    global-index Measurements + Partition (robot-major numbering)."""
+    from dcora_b200 import graph as pg
+    pp, pl, rg = meas.pp, meas.pl, meas.rg
+    A = num_robots or int(max([a.max() for a in (pp.r1, pp.r2, pl.r1, pl.r2, rg.r1, rg.r2)
+                               if len(a)]) + 1)
+    n_a = np.zeros(A, np.int64)
+    b_a = np.zeros(A, np.int64)
+
+    def upd(cnt, r_, p_, sel):
+        if sel.any():
+            np.maximum.at(cnt, r_[sel], p_[sel] + 1)
+    t = np.ones(len(pp), bool)
+    upd(n_a, pp.r1, pp.p1, t); upd(n_a, pp.r2, pp.p2, t)
+    t = np.ones(len(pl), bool)
+    upd(n_a, pl.r1, pl.p1, t); upd(b_a, pl.r2, pl.p2, t)
+    upd(n_a, rg.r1, rg.p1, rg.type1 == dataio.POSE); upd(n_a, rg.r2, rg.p2, rg.type2 == dataio.POSE)
+    upd(b_a, rg.r1, rg.p1, rg.type1 == dataio.LANDMARK)
+    upd(b_a, rg.r2, rg.p2, rg.type2 == dataio.LANDMARK)
+    poff = np.concatenate([[0], np.cumsum(n_a)])
+    boff = np.concatenate([[0], np.cumsum(b_a)])
+    n, b = int(poff[-1]), int(boff[-1])
+
+    def tv(r_, p_, ty):
+        return np.where(ty == dataio.POSE, poff[r_] + p_, n + boff[r_] + p_)
+    M = pg.Measurements(
+        d=meas.d, n=n, b=b,
+        pp_i=poff[pp.r1] + pp.p1, pp_j=poff[pp.r2] + pp.p2, pp_R=pp.R, pp_t=pp.t,
+        pp_kappa=pp.kappa, pp_tau=pp.tau, pp_w=pp.weight,
+        pl_i=poff[pl.r1] + pl.p1, pl_j=boff[pl.r2] + pl.p2, pl_t=pl.t, pl_tau=pl.tau,
+        pl_w=pl.weight,
+        rg_i=tv(rg.r1, rg.p1, rg.type1), rg_j=tv(rg.r2, rg.p2, rg.type2),
+        rg_range=rg.range, rg_prec=rg.precision, rg_w=rg.weight)
+    part = pg.Partition(A, np.repeat(np.arange(A), n_a), np.repeat(np.arange(A), b_a))
+    return M, part

@@ -1,0 +1,113 @@
+"""GPU parity tests of the multi-agent RBCD path (coupling product K8, public
+pack, batched coloured sweeps) against the oracle's one-agent-at-a-time
+restatement of examples/MultiRobotExample.cpp:223-307 / Agent::iterate."""
+import numpy as np
+import pytest
+
+from oracle import graph as og, manifold as mf, rbcd as orbcd, solver
+from tests.common import load_golden, product_measurements, rel_err, split_contiguous
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name, robots, r):
+    import dcora_b200 as dc
+    from dcora_b200 import graph as pg
+    if name.startswith("range_aided"):
+        meas, info = load_golden(name, prefix="local_")
+        ra = True
+    else:
+        meas, info = load_golden(name)
+        meas, _, _ = split_contiguous(meas, info["n"], robots)
+        ra = False
+    M, part = product_measurements(meas, robots)
+    gp = pg.GlobalProblem(M, part, ra=ra)
+    # oracle side: one Graph per agent (per-measurement restatement)
+    blocks = []
+    for a in range(robots):
+        g = og.Graph(a, r, meas.d, ra=ra).set_measurements(meas)
+        Q = g.quadratic_matrix()
+        L = mf.Layout(r, meas.d, g.n, g.l, g.b, ra=ra)
+        blocks.append(orbcd.AgentBlock(L, Q, int(gp.coff[a]), reg=og.precond_regularization(Q, ra)))
+    _, cross = gp.split(agents=[])
+    return gp, blocks, cross
+
+
+def _random_X(blocks, r, K, seed):
+    rng = np.random.default_rng(seed)
+    X = np.zeros((r, K))
+    for b in blocks:
+        X[:, b.c0:b.c1] = mf.random_point(b.L, rng)
+    return X
+
+
+@pytest.mark.parametrize("name,robots", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 2),
+                                         ("range_aided_slam_test_2d", 2)])
+def test_linear_term_and_cost_terms(name, robots):
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup(name, robots, r)
+    solver_gpu = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0))
+    X = _random_X(blocks, r, gp.K, 0)
+    solver_gpu.set_X(X)
+    o = orbcd.RBCD(blocks, cross)
+    o.set_X(X)
+    f_o, g_o = o.monitor()
+    f_g, g_g = solver_gpu.monitor()
+    assert abs(f_g - f_o) <= 1e-12 * abs(f_o)
+    assert abs(g_g - g_o) <= 1e-11 * abs(g_o)
+    # the RA preconditioner regularisation rule (Graph.cpp:1919-1960)
+    for a, b in enumerate(blocks):
+        assert abs(solver_gpu.P.precond_reg(a) - b.P.reg) <= 2e-3 * b.P.reg
+    # packed public columns == plain column gather
+    idx = np.arange(0, gp.K, 3, dtype=np.int32)
+    assert np.array_equal(solver_gpu.P.pack_columns(X, idx), X[:, idx])
+
+
+@pytest.mark.parametrize("name,robots,acc", [("smallGrid3D", 5, False),
+                                             ("range_aided_slam_test_3d", 2, False)])
+def test_sweeps_follow_the_oracle(name, robots, acc):
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup(name, robots, r)
+    X0 = _random_X(blocks, r, gp.K, 1)
+    G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0))
+    # same regularisation on both sides (the rule itself is checked above)
+    for a, b in enumerate(blocks):
+        b.P.reg = G.P.precond_reg(a)
+    O = orbcd.RBCD(blocks, cross, solver.ROptParameters())
+    G.set_X(X0)
+    O.set_X(X0)
+    colors = G.plan.colors
+    for it in range(3):
+        G.iterate()
+        O.sweep(colors)
+        Xg = G.get_X()
+        assert rel_err(Xg, O.X) < 1e-6, it
+    f_g, g_g = G.monitor()
+    f_o, g_o = O.monitor()
+    assert abs(f_g - f_o) <= 1e-7 * abs(f_o)
+
+
+def test_rbcd_converges_to_the_certified_optimum():
+    # smallGrid3D, 5 robots: RBCD drives the global problem to the known
+    # optimum 2f* = 1025.398052 (SE-Sync), the same value the centralised
+    # solve reaches (tests/test_gpu_solver.py)
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup("smallGrid3D", 5, r)
+    G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=1e-9,
+                                                  RTR_iterations=10, RTR_tCG_iterations=100))
+    G.set_X(_random_X(blocks, r, gp.K, 5))
+    f = gn = None
+    for it in range(400):
+        G.iterate()
+        if it % 10 == 9:
+            f, gn = G.monitor()
+            if gn < 1e-5:
+                break
+    assert gn < 1e-5
+    assert abs(2 * f - 1025.3980521) < 1e-6

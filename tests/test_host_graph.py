@@ -1,0 +1,119 @@
+"""CPU tests of the product's host-side data plumbing (dcora_b200/graph.py,
+rbcd.py planning) against the oracle's per-agent Graph restatement."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from dcora_b200 import graph as pg, rbcd, synthetic
+from oracle import graph as og, manifold as mf
+from tests.common import load_golden, product_measurements, split_contiguous
+
+
+def _csr(t, k):
+    return sp.csr_matrix((t[2], t[1], t[0]), shape=(k, k))
+
+
+def _multi(name, robots):
+    if name.startswith("range_aided"):
+        meas, info = load_golden(name, prefix="local_")
+        return meas, True
+    meas, info = load_golden(name)
+    m, counts, start = split_contiguous(meas, info["n"], robots)
+    return m, False
+
+
+CASES = [("smallGrid3D", 5), ("tinyGrid3D", 3), ("range_aided_slam_test_2d", 2),
+         ("range_aided_slam_test_3d", 2), ("kitti_00", 8)]
+
+
+@pytest.mark.parametrize("name,robots", CASES)
+def test_agent_Q_matches_oracle_graph(name, robots):
+    meas, ra = _multi(name, robots)
+    M, part = product_measurements(meas, robots)
+    gp = pg.GlobalProblem(M, part, ra=ra)
+    diag, cross = gp.split()
+    for a in range(robots):
+        g = og.Graph(a, 5, meas.d, ra=ra).set_measurements(meas)
+        assert (g.n, g.l, g.b) == (gp.n_a[a], gp.l_a[a], gp.b_a[a])
+        Qo = g.quadratic_matrix()
+        Qp = _csr(diag[a], g.k)
+        assert abs(Qo - Qp).max() <= 1e-12 * max(1.0, abs(Qo).max())
+
+
+@pytest.mark.parametrize("name,robots", CASES)
+def test_coupling_product_equals_oracle_linear_term(name, robots):
+    meas, ra = _multi(name, robots)
+    M, part = product_measurements(meas, robots)
+    gp = pg.GlobalProblem(M, part, ra=ra)
+    _, cross = gp.split(agents=[])
+    r = 5
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((r, gp.K))
+    G = (cross.T @ X.T).T          # G = X * C
+    graphs = [og.Graph(a, r, meas.d, ra=ra).set_measurements(meas) for a in range(robots)]
+    # neighbour dictionaries from X
+    nbr = {}
+    for a, g in enumerate(graphs):
+        Xa = X[:, gp.coff[a]:gp.coff[a + 1]]
+        for i in range(g.n):
+            nbr[("pose", a, i)] = np.column_stack([Xa[:, g.rot_cols(i)], Xa[:, g.trans_col(i)]])
+        for i in range(g.l):
+            nbr[("sph", a, i)] = Xa[:, g.sphere_col(i)]
+        for i in range(g.b):
+            nbr[("lmk", a, i)] = Xa[:, g.landmark_col(i)]
+    for a, g in enumerate(graphs):
+        Go = g.linear_matrix(nbr)
+        assert Go is not None
+        Gp = G[:, gp.coff[a]:gp.coff[a + 1]]
+        assert np.abs(Go - Gp).max() <= 1e-10 * max(1.0, np.abs(Go).max())
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_rank_plans_reproduce_G(world):
+    meas, ra = _multi("range_aided_slam_test_3d", 2) if world == 2 else _multi("smallGrid3D", 5)
+    robots = 2 if world == 2 else 5
+    M, part = product_measurements(meas, robots)
+    gp = pg.GlobalProblem(M, part, ra=ra)
+    _, cross = gp.split(agents=[])
+    plans = rbcd.make_plans(gp, world, cross)
+    r = 4
+    X = np.random.default_rng(0).standard_normal((r, gp.K))
+    G = (cross.T @ X.T).T
+    packs = [X[:, p.c0:p.c0 + p.K][:, p.pack_idx] for p in plans]
+    H = np.concatenate(packs, axis=1) if world > 1 else np.zeros((r, 0))
+    for p in plans:
+        XE = np.concatenate([X[:, p.c0:p.c0 + p.K], H], axis=1)
+        Gp = (p.coupling.T @ XE.T).T
+        assert np.abs(Gp - G[:, p.c0:p.c0 + p.K]).max() < 1e-12 * max(1.0, np.abs(G).max())
+    # colours: adjacent agents never share a colour
+    adj = gp.agent_graph(cross)
+    col = plans[0].colors
+    for a in range(gp.A):
+        assert all(col[a] != col[b] for b in adj[a])
+
+
+def test_synthetic_grid_is_consistent():
+    S = 6
+    meas, (Rgt, pos), idx = synthetic.grid3d(S, range_fraction=0.1, seed=1, noiseless=True)
+    n = S ** 3
+    assert meas.n == n and len(meas.pp_i) == 3 * S * S * (S - 1)
+    # consecutive poses on the path are grid neighbours and all carry an edge
+    key = set((meas.pp_i * n + meas.pp_j).tolist())
+    assert all((i * n + i + 1) in key for i in range(n - 1))
+    assert len(np.unique(meas.rg_i * n + meas.rg_j)) == len(meas.rg_i)
+    # noiseless data: the ground truth has zero cost
+    part = pg.Partition.contiguous(n, 4)
+    gp = pg.GlobalProblem(meas, part)
+    Q = gp.Q()
+    X = np.zeros((3, gp.K))
+    X[:, gp.rot_cols(np.arange(n)).reshape(-1)] = np.transpose(Rgt, (1, 0, 2)).reshape(3, -1)
+    X[:, gp.trans_col(np.arange(n))] = pos.T
+    e = np.arange(len(meas.rg_i))
+    dirs = (pos[meas.rg_i] - pos[meas.rg_j])
+    X[:, gp.sphere_col(e)] = (dirs / np.linalg.norm(dirs, axis=1)[:, None]).T
+    assert abs(np.sum((Q @ X.T).T * X)) < 1e-9
+    # the spanning-tree guess reproduces the ground truth up to the gauge
+    Ri, ti = synthetic.spanning_tree_init(meas, S, idx)
+    R0, p0 = Rgt[idx[0, 0, 0]], pos[idx[0, 0, 0]]
+    assert np.allclose(R0 @ Ri, Rgt, atol=1e-9)
+    assert np.allclose((R0 @ ti.T).T + p0, pos, atol=1e-9)
