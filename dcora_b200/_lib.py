@@ -91,6 +91,7 @@ SYMBOLS = {
     "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
                                                 c_uint8_p, VP]),
     "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
+    "dcora_problem_time_kernel": (C.c_int, [VP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "dcora_selfcheck_layout": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, c_double_p]),
     "dcora_selfcheck_cholesky": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,

@@ -353,10 +353,21 @@ class QuadraticProblem:
                                                      y.ptr, act, o.ptr))
         return out
 
+    def time_kernel(self, kind, iters=20):
+        """(mean ms, algorithmic bytes) of one application of a kernel class."""
+        ms, by = C.c_double(), C.c_double()
+        check(self.lib.dcora_problem_time_kernel(self.h, KERNELS[kind], iters,
+                                                 C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
     def time_spmm(self, iters=20):
         ms, by = C.c_double(), C.c_double()
         check(self.lib.dcora_problem_time_spmm(self.h, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+
+KERNELS = {"spmm": 0, "precond": 1, "project": 2, "retract": 3, "dot": 4, "axpby": 5,
+           "rhess": 6}
 
 
 class QuadraticOptimizer:

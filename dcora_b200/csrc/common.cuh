@@ -179,6 +179,7 @@ struct dcora_problem {
   size_t vec_len = 0;              // r*K doubles
   double *G = nullptr;             // internal layout (always allocated, zero if none)
   bool has_G = false;
+  bool timing_ready = false;       // WS_IO0 holds a feasible point for time_kernel
   std::vector<double *> ws;        // workspace vectors (internal layout)
   double *stage = nullptr;         // staging vector (reference layout)
   double *partials = nullptr;      // nchunks * NPART doubles

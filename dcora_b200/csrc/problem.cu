@@ -441,17 +441,68 @@ int dcora_problem_project_manifold(dcora_problem *p, const double *Mx, double *O
   return export_matrix(p, o, OUT, p->r);
 }
 
-int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
-                            double *algorithmic_bytes) {
+int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
+                              double *ms_mean, double *algorithmic_bytes) {
   DCORA_ENTER(p);
-  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
-  if (!x || !t) return DCORA_ERR_ALLOC;
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2), *s = p->vec(WS_S);
+  if (!x || !t || !o || !s) return DCORA_ERR_ALLOC;
+  const double rk = (double)p->r * (double)p->M->K;
+  double bytes = 0.0;
+  auto run = [&]() -> int {
+    switch (kind) {
+      case DCORA_KERNEL_SPMM:
+        bytes = 8.0 * (double)p->M->nnz_in + 16.0 * rk;
+        return launch_spmm(p, x, nullptr, t, -1);
+      case DCORA_KERNEL_PRECOND:
+        bytes = 2.0 * (8.0 * (double)p->M->F.nnzL + 16.0 * rk) + 24.0 * rk;
+        return launch_precond(p, x, t, o, -1);
+      case DCORA_KERNEL_PROJECT:
+        bytes = 24.0 * rk;
+        return launch_project_tangent(p, x, t, o, -1);
+      case DCORA_KERNEL_RETRACT:
+        bytes = 24.0 * rk;
+        return launch_retract(p, x, t, o, DCORA_RETRACT_QF, -1);
+      case DCORA_KERNEL_DOT: {
+        bytes = 16.0 * rk;
+        const double *xs[1] = {x}, *ys[1] = {t};
+        return launch_dots(p, 1, xs, ys, -1);
+      }
+      case DCORA_KERNEL_AXPBY:
+        bytes = 24.0 * rk;
+        return launch_axpby(p, o, -1, 0.5, x, -1, 0.25, t, -1);
+      case DCORA_KERNEL_RHESS:
+        bytes = 40.0 * rk;
+        return launch_rhess_correct(p, x, s, t, t, o, -1);
+      default:
+        set_error("dcora_problem_time_kernel: unknown kind");
+        return DCORA_ERR_ARG;
+    }
+  };
+  // a feasible point in x, something finite elsewhere
+  DCORA_CUDA(cudaMemsetAsync(t, 0, p->vec_len * sizeof(double), p->stream));
+  DCORA_CUDA(cudaMemsetAsync(s, 0, p->vec_len * sizeof(double), p->stream));
+  DCORA_TRY(launch_axpby(p, t, -1, 0.0, t, -1, 0.0, nullptr, -1));
+  if (!p->timing_ready) {
+    // deterministic pseudo-random start, projected to the manifold
+    std::vector<double> h(p->vec_len);
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    for (auto &v : h) {
+      st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+      v = (double)(st >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    }
+    DCORA_CUDA(cudaMemcpyAsync(t, h.data(), sizeof(double) * p->vec_len, cudaMemcpyHostToDevice,
+                               p->stream));
+    DCORA_CUDA(cudaStreamSynchronize(p->stream));
+    DCORA_TRY(launch_project_manifold(p, t, x, -1));
+    p->timing_ready = true;
+  }
+  DCORA_TRY(launch_copy(p, t, x, -1));
   cudaEvent_t e0, e1;
   DCORA_CUDA(cudaEventCreate(&e0));
   DCORA_CUDA(cudaEventCreate(&e1));
-  for (int i = 0; i < 3; ++i) DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
+  for (int i = 0; i < 3; ++i) DCORA_TRY(run());
   DCORA_CUDA(cudaEventRecord(e0, p->stream));
-  for (int i = 0; i < iters; ++i) DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
+  for (int i = 0; i < iters; ++i) DCORA_TRY(run());
   DCORA_CUDA(cudaEventRecord(e1, p->stream));
   DCORA_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
@@ -459,9 +510,13 @@ int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (ms_mean) *ms_mean = (double)ms / std::max(1, iters);
-  if (algorithmic_bytes)
-    *algorithmic_bytes = 8.0 * (double)p->M->nnz_in + 16.0 * (double)p->r * (double)p->M->K;
+  if (algorithmic_bytes) *algorithmic_bytes = bytes;
   return DCORA_OK;
+}
+
+int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
+                            double *algorithmic_bytes) {
+  return dcora_problem_time_kernel(p, DCORA_KERNEL_SPMM, iters, ms_mean, algorithmic_bytes);
 }
 
 }  // extern "C"

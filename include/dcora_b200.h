@@ -261,6 +261,20 @@ int dcora_problem_combine_project(dcora_problem *p, double a, const double *A,
  * (8*nnz(Q) + 16*r*K). */
 int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
                             double *algorithmic_bytes);
+/* The same for every hot-path kernel class: mean duration of one application
+ * on internally generated device-resident data (all agents active) and its
+ * algorithmic bytes as defined in SURVEY 8d / DESIGN.md:
+ *   SPMM     8 nnz(Q) + 16 rK            PRECOND  2 (8 nnz(L) + 16 rK) + 24 rK
+ *   PROJECT  24 rK   RETRACT 24 rK   DOT 16 rK   AXPBY 24 rK   RHESS 40 rK */
+#define DCORA_KERNEL_SPMM 0
+#define DCORA_KERNEL_PRECOND 1
+#define DCORA_KERNEL_PROJECT 2
+#define DCORA_KERNEL_RETRACT 3
+#define DCORA_KERNEL_DOT 4
+#define DCORA_KERNEL_AXPBY 5
+#define DCORA_KERNEL_RHESS 6
+int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
+                              double *ms_mean, double *algorithmic_bytes);
 
 /* Host-only self checks of the setup code (no GPU needed, no usable result):
  * max |Y_layout - Y_csr| of the CSR -> BSR/remainder conversion on internally
