@@ -97,6 +97,11 @@ SYMBOLS = {
     "dcora_selfcheck_cholesky": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,
                                            C.c_int32, C.c_int32, C.c_double, c_double_p,
                                            C.POINTER(C.c_int64)]),
+    "dcora_selfcheck_trsv": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,
+                                       C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                       c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdcora_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["layout.cpp", "chol.cpp", "selfcheck.cpp", "kernels.cu", "sptrsv.cu", "problem.cu",
+SOURCES = ["layout.cpp", "chol.cpp", "trsv_host.cpp", "selfcheck.cpp", "kernels.cu", "sptrsv.cu", "problem.cu",
            "solver.cu", "certify.cu", "rbcd.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
          "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr", "-diag-suppress", "128"]

@@ -95,11 +95,221 @@ std::vector<int> minimum_degree(int n, const std::vector<std::vector<int>> &adj,
   return order;
 }
 
+
+// ---------------------------------------------------------------------------
+// Nested dissection on the supervariable graph (George's automatic nested
+// dissection: separators are levels of a BFS level structure rooted at a
+// pseudo-peripheral node, thinned by one pass).  The recursion stops at
+// subgraphs of at most `leaf_weight` scalar rows.  Output: the elimination
+// order (subdomains first, separator last, recursively) and the partition of
+// that order into consecutive BLOCKS (leaf subdomains and separators): the
+// block triangular solve of sptrsv.cu inverts the diagonal blocks and walks
+// the (shallow, log-depth) block elimination tree level by level.
+struct NDContext {
+  const std::vector<std::vector<int>> *adj;
+  const std::vector<int> *weight;
+  int leaf_weight;
+  std::vector<int> label;     // region id of every node (-1: already ordered)
+  std::vector<int> dist;      // BFS scratch
+  std::vector<int> order;     // output
+  std::vector<int> block_ptr; // output: block boundaries in `order`
+  int next_label = 1;
+};
+
+static int region_weight(const NDContext &C, const std::vector<int> &nodes) {
+  int w = 0;
+  for (int v : nodes) w += (*C.weight)[v];
+  return w;
+}
+
+static void emit_block(NDContext &C, const std::vector<int> &nodes, int lab) {
+  if (nodes.empty()) return;
+  // interior nodes (no neighbour outside the block that is still unordered)
+  // first: keeps the fill of the ancestors' rows small
+  std::vector<int> inner, outer;
+  for (int v : nodes) {
+    bool boundary = false;
+    for (int u : (*C.adj)[v])
+      if (C.label[u] != lab && C.label[u] != -1) { boundary = true; break; }
+    (boundary ? outer : inner).push_back(v);
+  }
+  for (int v : inner) C.order.push_back(v);
+  for (int v : outer) C.order.push_back(v);
+  for (int v : nodes) C.label[v] = -1;
+  C.block_ptr.push_back((int)C.order.size());
+}
+
+// BFS inside region `lab` from `root`; returns the level structure.
+static void bfs_levels(NDContext &C, int root, int lab,
+                       std::vector<std::vector<int>> *levels) {
+  levels->clear();
+  levels->push_back(std::vector<int>(1, root));
+  C.dist[root] = 0;
+  std::vector<int> touched(1, root);
+  for (size_t lv = 0; lv < levels->size(); ++lv) {
+    std::vector<int> next;
+    for (int v : (*levels)[lv])
+      for (int u : (*C.adj)[v])
+        if (C.label[u] == lab && C.dist[u] < 0) {
+          C.dist[u] = (int)lv + 1;
+          next.push_back(u);
+          touched.push_back(u);
+        }
+    if (next.empty()) break;
+    levels->push_back(std::move(next));
+  }
+  for (int v : touched) C.dist[v] = -1;
+}
+
+static void nd_recurse(NDContext &C, std::vector<int> nodes, int lab) {
+  const std::vector<std::vector<int>> &adj = *C.adj;
+  const std::vector<int> &wt = *C.weight;
+  const int W = region_weight(C, nodes);
+  if (W <= C.leaf_weight || nodes.size() <= 1) { emit_block(C, nodes, lab); return; }
+  // ---- connected components of the region
+  std::vector<std::vector<int>> comps;
+  {
+    // label flipping marks visited nodes (temporary label -2)
+    for (int v : nodes) {
+      if (C.label[v] != lab) continue;
+      std::vector<int> comp(1, v);
+      C.label[v] = -2;
+      for (size_t h = 0; h < comp.size(); ++h)
+        for (int u : adj[comp[h]])
+          if (C.label[u] == lab) { C.label[u] = -2; comp.push_back(u); }
+      comps.push_back(std::move(comp));
+    }
+    for (int v : nodes) C.label[v] = lab;
+  }
+  if (comps.size() > 1) {
+    // two bins of components, balanced greedily; no separator needed
+    std::sort(comps.begin(), comps.end(),
+              [&](const std::vector<int> &a, const std::vector<int> &b) {
+                return a.size() > b.size();
+              });
+    std::vector<int> binA, binB;
+    int wa = 0, wb = 0;
+    for (auto &c : comps) {
+      const int w = region_weight(C, c);
+      if (wa <= wb) { binA.insert(binA.end(), c.begin(), c.end()); wa += w; }
+      else { binB.insert(binB.end(), c.begin(), c.end()); wb += w; }
+    }
+    const int la = C.next_label++, lb = C.next_label++;
+    for (int v : binA) C.label[v] = la;
+    for (int v : binB) C.label[v] = lb;
+    nd_recurse(C, std::move(binA), la);
+    nd_recurse(C, std::move(binB), lb);
+    return;
+  }
+  // ---- pseudo-peripheral root
+  int root = nodes[0];
+  {
+    size_t best = adj[root].size();
+    for (int v : nodes)
+      if (adj[v].size() < best) { best = adj[v].size(); root = v; }
+  }
+  std::vector<std::vector<int>> levels;
+  bfs_levels(C, root, lab, &levels);
+  for (int it = 0; it < 6; ++it) {
+    const std::vector<int> &last = levels.back();
+    int cand = last[0];
+    size_t deg = adj[cand].size();
+    for (int v : last)
+      if (adj[v].size() < deg) { deg = adj[v].size(); cand = v; }
+    std::vector<std::vector<int>> lv2;
+    bfs_levels(C, cand, lab, &lv2);
+    if (lv2.size() > levels.size()) { levels.swap(lv2); root = cand; }
+    else break;
+  }
+  const int h = (int)levels.size();
+  if (h < 3) {
+    // no interior level (star / clique-like region).  Small: one dense block.
+    // Large: peel the highest-degree node off as a one-node separator (it is
+    // what keeps the region's diameter small) and dissect the rest.
+    if (W <= 4 * C.leaf_weight) { emit_block(C, nodes, lab); return; }
+    int hub = nodes[0];
+    size_t hd = 0;
+    for (int v : nodes) {
+      size_t dg = 0;
+      for (int u : adj[v]) dg += C.label[u] == lab;
+      if (dg > hd) { hd = dg; hub = v; }
+    }
+    std::vector<int> rest;
+    rest.reserve(nodes.size() - 1);
+    const int lr = C.next_label++;
+    for (int v : nodes)
+      if (v != hub) { rest.push_back(v); C.label[v] = lr; }
+    nd_recurse(C, std::move(rest), lr);
+    emit_block(C, std::vector<int>(1, hub), lab);
+    return;
+  }
+  // ---- choose the separator level
+  std::vector<int> lw(h, 0), cum(h + 1, 0);
+  for (int i = 0; i < h; ++i) {
+    for (int v : levels[i]) lw[i] += wt[v];
+    cum[i + 1] = cum[i] + lw[i];
+  }
+  int best = -1;
+  double best_cost = 0.0;
+  for (int pass = 0; pass < 2 && best < 0; ++pass)
+    for (int i = 1; i + 1 < h; ++i) {
+      const int below = cum[i], above = W - cum[i + 1];
+      const double bal = (double)std::min(below, above) / (double)std::max(1, std::max(below, above));
+      if (pass == 0 && bal < 0.4) continue;
+      const double cost = (double)lw[i] * (1.0 + 0.5 * (1.0 - bal)) + (pass ? 1e6 * (1.0 - bal) : 0.0);
+      if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
+    }
+  // ---- thin it: separator nodes without a neighbour in the next level join
+  // the lower part
+  std::vector<int> sep, partA, partB;
+  for (int i = 0; i < best; ++i) partA.insert(partA.end(), levels[i].begin(), levels[i].end());
+  for (int i = best + 1; i < h; ++i) partB.insert(partB.end(), levels[i].begin(), levels[i].end());
+  const int la = C.next_label++, lb = C.next_label++;
+  for (int v : partB) C.label[v] = lb;
+  for (int v : levels[best]) {
+    bool up = false;
+    for (int u : adj[v])
+      if (C.label[u] == lb) { up = true; break; }
+    if (up) sep.push_back(v); else partA.push_back(v);
+  }
+  for (int v : partA) C.label[v] = la;
+  // separator keeps label `lab`
+  nd_recurse(C, std::move(partA), la);
+  nd_recurse(C, std::move(partB), lb);
+  emit_block(C, sep, lab);
+}
+
+void nested_dissection(int n, const std::vector<std::vector<int>> &adj,
+                       const std::vector<int> &weight, int leaf_weight,
+                       std::vector<int> *order, std::vector<int> *block_ptr) {
+  NDContext C;
+  C.adj = &adj;
+  C.weight = &weight;
+  C.leaf_weight = leaf_weight;
+  C.label.assign(n, 0);
+  C.dist.assign(n, -1);
+  C.order.reserve(n);
+  C.block_ptr.assign(1, 0);
+  // hubs (e.g. a landmark ranged from thousands of poses) would make every
+  // BFS level structure two levels deep: order them last, as the top block
+  size_t total_deg = 0;
+  for (int v = 0; v < n; ++v) total_deg += adj[v].size();
+  const size_t hub_deg = std::max<size_t>(64, 10 * (total_deg / std::max(1, n) + 1));
+  std::vector<int> all, hubs;
+  for (int v = 0; v < n; ++v) (adj[v].size() > hub_deg ? hubs : all).push_back(v);
+  const int hub_label = C.next_label++;
+  for (int v : hubs) C.label[v] = hub_label;
+  nd_recurse(C, std::move(all), 0);
+  emit_block(C, hubs, hub_label);
+  order->swap(C.order);
+  block_ptr->swap(C.block_ptr);
+}
+
 }  // namespace
 
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
                     const std::vector<double> &Ax, int dh, int npose,
-                    HostFactor *out) {
+                    HostFactor *out, int ordering, int leaf_rows) {
   HostFactor &F = *out;
   F.k = k;
   // ---- supervariable graph
@@ -130,13 +340,34 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
   }
   std::vector<int> weight(nsv);
   for (int s = 0; s < nsv; ++s) weight[s] = s < npose ? dh : 1;
-  const std::vector<int> order = minimum_degree(nsv, adj, weight);
+  std::vector<int> order, sv_block_ptr;
+  if (ordering == DCORA_ORDERING_ND) {
+    nested_dissection(nsv, adj, weight, leaf_rows, &order, &sv_block_ptr);
+  } else {
+    order = minimum_degree(nsv, adj, weight);
+    sv_block_ptr.resize(nsv + 1);
+    std::iota(sv_block_ptr.begin(), sv_block_ptr.end(), 0);
+  }
   F.perm.clear();
   F.perm.reserve(k);
-  for (int s : order) {
-    const int c0 = s < npose ? s * dh : npc + (s - npose);
-    const int c1 = s < npose ? c0 + dh : c0 + 1;
-    for (int c = c0; c < c1; ++c) F.perm.push_back(c);
+  F.pose_start.assign(k, -1);
+  F.blk_ptr.assign(1, 0);
+  {
+    size_t nb = 1;
+    for (int t = 0; t < nsv; ++t) {
+      const int s = order[t];
+      const int c0 = s < npose ? s * dh : npc + (s - npose);
+      const int c1 = s < npose ? c0 + dh : c0 + 1;
+      const int first = (int)F.perm.size();
+      for (int c = c0; c < c1; ++c) {
+        if (s < npose) F.pose_start[F.perm.size()] = first;
+        F.perm.push_back(c);
+      }
+      if (nb < sv_block_ptr.size() && t + 1 == sv_block_ptr[nb]) {
+        F.blk_ptr.push_back((int)F.perm.size());
+        ++nb;
+      }
+    }
   }
   std::vector<int> pinv(k);
   for (int i = 0; i < k; ++i) pinv[F.perm[i]] = i;
@@ -229,6 +460,7 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
     F.Li[q] = j;
     F.Lx[q] = std::sqrt(d);
   }
+  F.nnz = nnzL;
   return DCORA_OK;
 }
 

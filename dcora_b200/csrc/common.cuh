@@ -104,38 +104,54 @@ struct DeviceCoupling {
 };
 
 // Host sparse Cholesky factor of one agent (chol.cpp), internal ordering.
+constexpr int DCORA_ORDERING_MD = 0;  // minimum degree, one block per supervariable
+constexpr int DCORA_ORDERING_ND = 1;  // nested dissection, blocks = subdomains / separators
+constexpr int TRSV_LEAF_ROWS = 32;    // ND recursion stops at subdomains of <= 32 rows
 struct HostFactor {
   int k = 0;
   std::vector<int> perm;            // new -> old (internal col within agent)
   std::vector<int> Lp, Li;          // CSC of L (k+1, nnz), rows sorted
   std::vector<double> Lx;
+  int64_t nnz = 0;                  // nnz(L) (kept after Li / Lx are released)
+  std::vector<int> blk_ptr;         // factor-row boundaries of the diagonal blocks
+  std::vector<int> pose_start;      // k: first factor row of the row's pose block, -1 if scalar
 };
 // A given as full symmetric CSR (internal ordering, agent-local); `dh` and
 // `npose` describe the supervariable structure used by the ordering.
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
                     const std::vector<double> &Ax, int dh, int npose,
-                    HostFactor *out);
+                    HostFactor *out, int ordering = DCORA_ORDERING_ND,
+                    int leaf_rows = TRSV_LEAF_ROWS);
 
 double lambda_max_lanczos(int k, const int *Ap, const int *Ai, const double *Ax,
                           double tol, int max_steps);
 
-// Device-side factor for the whole batch (sptrsv.cu).
+// Device-side block triangular-solve schedule for the whole batch (sptrsv.cu;
+// the host-side twin and the meaning of every array are in trsv.h).
+struct TrsvLevel;
+struct DeviceTrsvDir {
+  int *ta_row = nullptr, *ta_bptr = nullptr, *bcol = nullptr;
+  double *bval = nullptr;
+  int *srowptr = nullptr, *scol = nullptr;
+  double *sval = nullptr;
+  int *sb_row0 = nullptr, *sb_w = nullptr, *sb_direct = nullptr;
+  long long *sb_off = nullptr;
+  int *lb_row0 = nullptr, *lb_w = nullptr, *lb_direct = nullptr;
+  long long *lb_off = nullptr;
+  int *lr_blk = nullptr, *lr_i = nullptr;
+  double *dense = nullptr;
+  TrsvLevel *levels = nullptr;
+  int *lvl0 = nullptr;  // A + 1 offsets into levels
+};
 struct DeviceFactor {
   bool present = false;
-  int64_t nnzL = 0;
+  int64_t nnzL = 0;           // nnz of the scalar Cholesky factor
+  int64_t stored_values = 0;  // values one direction of the schedule stores
   int A = 0;
-  // forward: rows of L (CSR, strictly-lower part + inverse diagonal)
-  int *rowptr = nullptr, *colidx = nullptr;
-  double *val = nullptr;
-  // backward: rows of L^T == columns of L (CSC)
-  int *t_rowptr = nullptr, *t_colidx = nullptr;
-  double *t_val = nullptr;
-  double *inv_diag = nullptr;  // K
-  int *perm = nullptr;         // K: factor row (global) -> internal column
-  // level schedules, per agent: rows sorted by level
-  int *fwd_rows = nullptr, *bwd_rows = nullptr;        // K each (global row ids)
-  int *fwd_lvlptr = nullptr, *bwd_lvlptr = nullptr;    // concatenated per agent
-  int *fwd_lvl0 = nullptr, *bwd_lvl0 = nullptr;        // A+1 offsets into lvlptr
+  int cluster = 1;            // CTAs per agent
+  int max_levels = 0;
+  DeviceTrsvDir dir[2];       // forward (L), backward (L^T)
+  int *perm = nullptr;        // K: factor row (global) -> internal column
   void release();
 };
 

@@ -75,13 +75,14 @@ int launch_reduce_scalars(dcora_problem *p, int nslots, const int *dst_slots);
 // preconditioner application z = proj_X( (Q+reg I)^-1 v ) (sptrsv.cu)
 int launch_precond(dcora_problem *p, const double *X, const double *V, double *OUT,
                    int mask_flag);
+struct AgentTrsv;
 int upload_factor(dcora::DeviceMatrices *M, const std::vector<HostFactor> &F,
-                  const HostLayout &H);
+                  std::vector<AgentTrsv> &schedules, const HostLayout &H);
 
 // workspace vector indices (p->vec(i))
 enum Ws : int {
   WS_X1 = 0, WS_X2, WS_EG, WS_GF, WS_S, WS_ETA, WS_DELTA, WS_HD, WS_R, WS_Z,
-  WS_T0, WS_T1, WS_TRSV_PANEL, WS_TRSV_SOL, WS_IO0, WS_IO1, WS_IO2, WS_COUNT
+  WS_T0, WS_T1, WS_TRSV_PANEL, WS_TRSV_TMP, WS_TRSV_SOL, WS_IO0, WS_IO1, WS_IO2, WS_COUNT
 };
 
 }  // namespace dcora

@@ -7,6 +7,7 @@
 
 #include "kernels.cuh"
 #include "solver.cuh"
+#include "trsv.h"
 
 namespace dcora {
 
@@ -221,6 +222,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
   M->reg.assign(num_agents, -1.0);
   if (any) {
     std::vector<HostFactor> HF(num_agents);
+    std::vector<AgentTrsv> AT(num_agents);
     std::vector<int> rcs(num_agents, DCORA_OK);
     const int dh = d + 1;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -261,13 +263,22 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       // triangle only inside sparse_cholesky (as CHOLMOD does for symmetric
       // input).
       rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a]);
+      if (rcs[a] == DCORA_OK) {
+        rcs[a] = build_agent_trsv(HF[a], dh, &AT[a]);
+        // only nnz(L) and the permutation are needed from here on
+        const size_t nnz = HF[a].Lx.size();
+        std::vector<int>().swap(HF[a].Li);
+        std::vector<double>().swap(HF[a].Lx);
+        HF[a].Lx.resize(0);
+        HF[a].nnz = (int64_t)nnz;
+      }
     }
     for (int a = 0; a < num_agents; ++a)
       if (rcs[a] != DCORA_OK) {
         set_error("Cholesky factorisation of Q + reg*I failed for agent " + std::to_string(a));
         return DCORA_ERR_FACTOR;
       }
-    DCORA_TRY(upload_factor(M.get(), HF, H));
+    DCORA_TRY(upload_factor(M.get(), HF, AT, H));
   }
 
   dcora_problem *p = new dcora_problem();

@@ -288,6 +288,19 @@ int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const int32_t *co
                              double reg, double *rel_residual,
                              int64_t *factor_nnz);
 
+/* Host self check of the block triangular-solve schedule the preconditioner
+ * kernel walks (nested-dissection factor regrouped into inverted diagonal
+ * blocks + off-diagonal pose blocks, replayed sequentially on the host):
+ * relative residual of (Q + reg I) x = b, nnz(L), values stored by the
+ * schedule, number of diagonal blocks and block-tree depth per direction.
+ * ordering: 0 = minimum degree (one block per supervariable), 1 = nested
+ * dissection (what dcora_problem_create uses). */
+int dcora_selfcheck_trsv(int32_t k, const int32_t *rowptr, const int32_t *col,
+                         const double *val, int32_t dh, int32_t npose, double reg,
+                         int32_t ordering, double *rel_residual, int64_t *factor_nnz,
+                         int64_t *stored_values, int32_t *nblocks,
+                         int32_t *levels_fwd, int32_t *levels_bwd);
+
 #ifdef __cplusplus
 }
 #endif

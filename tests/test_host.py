@@ -99,3 +99,55 @@ def test_cholesky_rejects_indefinite(lib):
                                       v.ctypes.data_as(_lib.c_double_p), 1, 0, 0.0,
                                       C.byref(res), C.byref(nnz))
     assert rc == -4
+
+
+def _internal_order(P, info):
+    """Q in the library's internal column order (pose blocks, spheres,
+    landmarks) -- dcora_b200/csrc/layout.cpp."""
+    import scipy.sparse as sp
+    Q = P.Q.tocsr()
+    L = P.L
+    if not L.ra:
+        return Q
+    k, d, n, l = L.k, info["d"], L.n, L.l
+    c = np.arange(k)
+    m = np.empty(k, dtype=np.int64)
+    dn = d * n
+    rot = c < dn
+    m[rot] = (c[rot] // d) * (d + 1) + c[rot] % d
+    sph = (c >= dn) & (c < dn + l)
+    m[sph] = (d + 1) * n + (c[sph] - dn)
+    tr = (c >= dn + l) & (c < dn + l + n)
+    m[tr] = (c[tr] - dn - l) * (d + 1) + d
+    lm = c >= dn + l + n
+    m[lm] = (d + 1) * n + l + (c[lm] - dn - l - n)
+    Pm = sp.csr_matrix((np.ones(k), (m, c)), shape=(k, k))
+    Q = (Pm @ Q @ Pm.T).tocsr()
+    Q.sort_indices()
+    return Q
+
+
+@pytest.mark.parametrize("ordering", [0, 1])
+@pytest.mark.parametrize("name", ["tinyGrid3D", "smallGrid3D", "sphere2500", "city10000",
+                                  "kitti_00", "tiers", "range_aided_slam_test_3d",
+                                  "range_aided_slam_test_2d"])
+def test_block_trsv_schedule(lib, name, ordering):
+    """The nested-dissection block schedule the preconditioner kernel walks
+    solves (Q + reg I) x = b (replayed sequentially on the host)."""
+    P, g, info = central_problem(name, 3)
+    Q = _internal_order(P, info)
+    rp, ci, v = Q.indptr.astype(np.int32), Q.indices.astype(np.int32), Q.data.astype(np.float64)
+    res, nnz, stored = C.c_double(), C.c_int64(), C.c_int64()
+    nb, lf, lb = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.dcora_selfcheck_trsv(Q.shape[0], rp.ctypes.data_as(_lib.c_int32_p),
+                                  ci.ctypes.data_as(_lib.c_int32_p),
+                                  v.ctypes.data_as(_lib.c_double_p), info["d"] + 1, P.L.n,
+                                  P.reg, ordering, C.byref(res), C.byref(nnz), C.byref(stored),
+                                  C.byref(nb), C.byref(lf), C.byref(lb))
+    assert rc == 0
+    assert res.value < 1e-9
+    assert stored.value >= nnz.value - Q.shape[0] * 0 - 1 or stored.value > 0
+    assert lf.value == lb.value >= 1
+    if ordering == 1 and Q.shape[0] > 2000:
+        # the block elimination tree of the ND ordering is shallow
+        assert lf.value <= 64, (lf.value, nb.value)
