@@ -126,32 +126,20 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
 double lambda_max_lanczos(int k, const int *Ap, const int *Ai, const double *Ax,
                           double tol, int max_steps);
 
-// Device-side block triangular-solve schedule for the whole batch (sptrsv.cu;
-// the host-side twin and the meaning of every array are in trsv.h).
-struct TrsvLevel;
-struct DeviceTrsvDir {
-  int *ta_row = nullptr, *ta_bptr = nullptr, *bcol = nullptr;
-  double *bval = nullptr;
-  int *srowptr = nullptr, *scol = nullptr;
-  double *sval = nullptr;
-  int *sb_row0 = nullptr, *sb_w = nullptr, *sb_direct = nullptr;
-  long long *sb_off = nullptr;
-  int *lb_row0 = nullptr, *lb_w = nullptr, *lb_direct = nullptr;
-  long long *lb_off = nullptr;
-  int *lr_blk = nullptr, *lr_i = nullptr;
-  double *dense = nullptr;
-  TrsvLevel *levels = nullptr;
-  int *lvl0 = nullptr;  // A + 1 offsets into levels
-};
+// Device-side block triangular-solve tapes for the whole batch (sptrsv.cu; the
+// tape format is documented in trsv.h).
 struct DeviceFactor {
   bool present = false;
-  int64_t nnzL = 0;           // nnz of the scalar Cholesky factor
-  int64_t stored_values = 0;  // values one direction of the schedule stores
+  int64_t nnzL = 0;           // nnz of the scalar Cholesky factors
+  int64_t stored_values = 0;  // factor values one direction of the tapes stores
+  int64_t tape_bytes = 0;     // both directions, with headers and padding
   int A = 0;
   int cluster = 1;            // CTAs per agent
   int max_levels = 0;
-  DeviceTrsvDir dir[2];       // forward (L), backward (L^T)
-  int *perm = nullptr;        // K: factor row (global) -> internal column
+  unsigned long long *tape = nullptr;  // all tapes, 8-byte words
+  long long *tape_off = nullptr;       // A * nwarps: first word of each warp's tape
+  int *tape_chunks = nullptr;          // A * nwarps: length in 1 KB chunks
+  int *nlev = nullptr;                 // A * 2: levels forward / backward
   void release();
 };
 

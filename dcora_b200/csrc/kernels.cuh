@@ -74,10 +74,12 @@ int launch_reduce_scalars(dcora_problem *p, int nslots, const int *dst_slots);
 
 // preconditioner application z = proj_X( (Q+reg I)^-1 v ) (sptrsv.cu)
 int launch_precond(dcora_problem *p, const double *X, const double *V, double *OUT,
-                   int mask_flag);
-struct AgentTrsv;
+                   int mask_flag, unsigned long long *trace = nullptr, int trace_agent = 0);
+struct AgentTape;
 int upload_factor(dcora::DeviceMatrices *M, const std::vector<HostFactor> &F,
-                  std::vector<AgentTrsv> &schedules, const HostLayout &H);
+                  std::vector<AgentTape> &tapes, int cluster, const HostLayout &H);
+int trsv_cluster_for(double rows_per_agent);  // CTAs per agent
+int trsv_warps_per_cta();
 
 // workspace vector indices (p->vec(i))
 enum Ws : int {

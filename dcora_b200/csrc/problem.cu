@@ -122,7 +122,10 @@ using namespace dcora;
 double *dcora_problem::vec(int i) {
   if (i < 0 || i >= (int)ws.size()) return nullptr;
   if (!ws[i]) {
-    if (cudaMalloc(&ws[i], std::max<size_t>(1, vec_len) * sizeof(double)) != cudaSuccess) {
+    // zero-filled: the triangular-solve panels are read through (d+1)-row
+    // windows whose unused rows meet zero coefficients and must be finite
+    if (cudaMalloc(&ws[i], std::max<size_t>(1, vec_len) * sizeof(double)) != cudaSuccess ||
+        cudaMemsetAsync(ws[i], 0, std::max<size_t>(1, vec_len) * sizeof(double), stream) != cudaSuccess) {
       set_error("workspace allocation failed");
       ws[i] = nullptr;
     }
@@ -222,7 +225,13 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
   M->reg.assign(num_agents, -1.0);
   if (any) {
     std::vector<HostFactor> HF(num_agents);
-    std::vector<AgentTrsv> AT(num_agents);
+    std::vector<AgentTape> AT(num_agents);
+    // launch cluster = the largest agent's; every agent's own split depends
+    // only on its size
+    int cluster = 1;
+    for (int a = 0; a < num_agents; ++a)
+      cluster = std::max(cluster, trsv_cluster_for((double)(H.coff[a + 1] - H.coff[a])));
+    const int tape_warps = cluster * trsv_warps_per_cta();
     std::vector<int> rcs(num_agents, DCORA_OK);
     const int dh = d + 1;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -264,7 +273,8 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       // input).
       rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a]);
       if (rcs[a] == DCORA_OK) {
-        rcs[a] = build_agent_trsv(HF[a], dh, &AT[a]);
+        rcs[a] = build_agent_tape(HF[a], dh, trsv_cluster_for((double)k) * trsv_warps_per_cta(),
+                                  tape_warps, c0, &AT[a]);
         // only nnz(L) and the permutation are needed from here on
         const size_t nnz = HF[a].Lx.size();
         std::vector<int>().swap(HF[a].Li);
@@ -278,7 +288,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
         set_error("Cholesky factorisation of Q + reg*I failed for agent " + std::to_string(a));
         return DCORA_ERR_FACTOR;
       }
-    DCORA_TRY(upload_factor(M.get(), HF, AT, H));
+    DCORA_TRY(upload_factor(M.get(), HF, AT, cluster, H));
   }
 
   dcora_problem *p = new dcora_problem();
@@ -522,6 +532,34 @@ int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
   cudaEventDestroy(e1);
   if (ms_mean) *ms_mean = (double)ms / std::max(1, iters);
   if (algorithmic_bytes) *algorithmic_bytes = bytes;
+  return DCORA_OK;
+}
+
+int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, int32_t all_agents,
+                           uint64_t *stamps, int32_t max_stamps) {
+  DCORA_ENTER(p);
+  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!x || !t || !o || !stamps || max_stamps < 4) return DCORA_ERR_ARG;
+  if (!p->timing_ready) {
+    double ms, by;
+    DCORA_TRY(dcora_problem_time_kernel(p, DCORA_KERNEL_PROJECT, 1, &ms, &by));
+  }
+  unsigned long long *d = nullptr;
+  DCORA_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * max_stamps));
+  DCORA_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * max_stamps, p->stream));
+  int mask = -1;
+  if (!all_agents) {
+    std::vector<uint8_t> act(p->M->A, 0);
+    act[agent] = 1;
+    DCORA_TRY(set_user_mask(p, act.data()));
+    mask = F_USER;
+  }
+  for (int it = 0; it < 3; ++it) DCORA_TRY(launch_precond(p, x, t, o, mask, d, agent));
+  DCORA_CUDA(cudaMemcpyAsync(stamps, d, sizeof(unsigned long long) * max_stamps,
+                             cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  cudaFree(d);
+  if (!all_agents) DCORA_TRY(set_user_mask(p, nullptr));
   return DCORA_OK;
 }
 

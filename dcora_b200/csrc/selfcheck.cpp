@@ -3,6 +3,7 @@
 // not produce results a caller could use instead of the GPU path.
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -106,19 +107,9 @@ extern "C" int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const 
 
 #include "trsv.h"
 
-// Host self check of the block triangular-solve schedule (trsv_host.cpp): the
-// factor of Q + reg*I is built with the requested ordering, regrouped into the
-// device schedule, and that schedule is replayed sequentially on the host for
-// an internally generated right-hand side.  Reports the relative residual
-// ||(Q + reg I) x - b|| / ||b||, nnz(L), the number of values the schedule
-// stores (zero-padded pose blocks + inverted diagonal blocks), the number of
-// diagonal blocks and the depth of the block elimination tree per direction.
-extern "C" int dcora_selfcheck_trsv(int32_t k, const int32_t *rowptr, const int32_t *col,
-                                    const double *val, int32_t dh, int32_t npose,
-                                    double reg, int32_t ordering, double *rel_residual,
-                                    int64_t *factor_nnz, int64_t *stored_values,
-                                    int32_t *nblocks, int32_t *levels_fwd,
-                                    int32_t *levels_bwd) {
+static int factor_for_check(int32_t k, const int32_t *rowptr, const int32_t *col,
+                            const double *val, int32_t dh, int32_t npose, double reg,
+                            int32_t ordering, HostFactor *F) {
   std::vector<int> Bp(k + 1, 0), Ai;
   std::vector<double> Ax;
   for (int i = 0; i < k; ++i) Bp[i + 1] = Bp[i] + (rowptr[i + 1] - rowptr[i]) + 1;
@@ -128,27 +119,36 @@ extern "C" int dcora_selfcheck_trsv(int32_t k, const int32_t *rowptr, const int3
     for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) { Ai[w] = col[p]; Ax[w] = val[p]; ++w; }
     Ai[w] = i; Ax[w] = reg;
   }
+  return sparse_cholesky(k, Bp, Ai, Ax, dh, npose, F, ordering, TRSV_LEAF_ROWS);
+}
+
+// Host self check of the block triangular-solve tapes (trsv_host.cpp): the
+// factor of Q + reg*I is built with the requested ordering, compiled into the
+// per-warp tapes the kernel streams, and the tapes are replayed sequentially on
+// the host for an internally generated right-hand side.  Reports the relative
+// residual ||(Q + reg I) x - b|| / ||b||, nnz(L), the number of factor values
+// on the tapes per direction (zero-padded pose blocks + inverted diagonal
+// blocks), the number of diagonal blocks and the depth of the block
+// elimination tree per direction.
+extern "C" int dcora_selfcheck_trsv(int32_t k, const int32_t *rowptr, const int32_t *col,
+                                    const double *val, int32_t dh, int32_t npose,
+                                    double reg, int32_t ordering, double *rel_residual,
+                                    int64_t *factor_nnz, int64_t *stored_values,
+                                    int32_t *nblocks, int32_t *levels_fwd,
+                                    int32_t *levels_bwd) {
   HostFactor F;
-  DCORA_TRY(sparse_cholesky(k, Bp, Ai, Ax, dh, npose, &F, ordering, TRSV_LEAF_ROWS));
-  AgentTrsv S;
-  DCORA_TRY(build_agent_trsv(F, dh, &S));
+  DCORA_TRY(factor_for_check(k, rowptr, col, val, dh, npose, reg, ordering, &F));
+  AgentTape S;
+  DCORA_TRY(build_agent_tape(F, dh, 48, 64, 0, &S));
   if (factor_nnz) *factor_nnz = (int64_t)F.Lx.size();
-  if (stored_values) {
-    int64_t s = 0;
-    for (int dir = 0; dir < 1; ++dir)
-      s += (int64_t)S.dir[dir].bval.size() + (int64_t)S.dir[dir].sval.size() +
-           (int64_t)S.dir[dir].dense.size();
-    *stored_values = s;
-  }
+  if (stored_values) *stored_values = S.stored_values / 2;
   if (nblocks) *nblocks = S.nblocks;
-  if (levels_fwd) *levels_fwd = (int32_t)S.dir[0].levels.size();
-  if (levels_bwd) *levels_bwd = (int32_t)S.dir[1].levels.size();
+  if (levels_fwd) *levels_fwd = S.nlev[0];
+  if (levels_bwd) *levels_bwd = S.nlev[1];
   uint64_t st = 7654321ull;
-  std::vector<double> b(k), pb(k), y(k), x(k);
+  std::vector<double> b(k), x(k, 0.0), T(k + 8, 0.0), Y(k + 8, 0.0);
   for (auto &v : b) v = prand(st);
-  for (int i = 0; i < k; ++i) pb[i] = b[F.perm[i]];
-  agent_trsv_apply_host(S, dh, pb.data(), y.data());
-  for (int i = 0; i < k; ++i) x[F.perm[i]] = y[i];
+  agent_tape_apply_host(S, b.data(), x.data(), T.data(), Y.data());
   double rn = 0.0, bn = 0.0;
   for (int i = 0; i < k; ++i) {
     double s = reg * x[i];

@@ -4,17 +4,19 @@
 //
 // Schedule (trsv_host.cpp): the factor is grouped by the nested-dissection
 // blocks; per level of the (log-depth) block elimination tree
-//   phase A  t_B = rhs_B - M[B, solved] y     sparse rows: (d+1)x(d+1) pose
-//                                             blocks + scalar remainder
+//   phase A  t_B = rhs_B - M[B, solved] y     (d+1)x(d+1) off-diagonal blocks
 //   phase B  y_B = D_B t_B                    dense packed triangular inverse
 // forward with M = L, then backward with M = L^T, in ONE launch.
 //
-// One thread-block CLUSTER per agent (up to 8 CTAs x 512 threads = 128 warps
-// on 8 SMs of one GPC): the tasks of a phase are spread over all warps of the
-// cluster and phases are separated by the hardware cluster barrier, so agents
-// never wait for each other and an agent is not limited to one SM's load
-// bandwidth.  The r right-hand sides are processed together; the solution
-// panel is (factor row, r) row-major, the same memory shape as every vector.
+// One thread-block CLUSTER per agent (up to 8 CTAs x 8 warps on 8 SMs of one
+// GPC); phases are separated by the hardware cluster barrier, so agents never
+// wait for each other.  Every warp executes its own pre-compiled TAPE (trsv.h):
+// the factor values arrive in consumption order through a per-warp shared-
+// memory ring that is filled by bulk asynchronous copies (cp.async.bulk +
+// mbarrier, i.e. TMA) running up to 8 KB ahead of the consumer and straight
+// through the level barriers; only the gathers from the solution panel wait
+// for a barrier.  The r right-hand sides are processed together; the panel is
+// (factor row, r) row-major, the same memory shape as every other vector.
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
@@ -25,23 +27,24 @@ namespace cg = cooperative_groups;
 namespace dcora {
 
 void DeviceFactor::release() {
-  for (int d = 0; d < 2; ++d) {
-    DeviceTrsvDir &T = dir[d];
-    cudaFree(T.ta_row); cudaFree(T.ta_bptr); cudaFree(T.bcol); cudaFree(T.bval);
-    cudaFree(T.srowptr); cudaFree(T.scol); cudaFree(T.sval);
-    cudaFree(T.sb_row0); cudaFree(T.sb_w); cudaFree(T.sb_direct); cudaFree(T.sb_off);
-    cudaFree(T.lb_row0); cudaFree(T.lb_w); cudaFree(T.lb_direct); cudaFree(T.lb_off);
-    cudaFree(T.lr_blk); cudaFree(T.lr_i); cudaFree(T.dense);
-    cudaFree(T.levels); cudaFree(T.lvl0);
-  }
-  cudaFree(perm);
+  cudaFree(tape); cudaFree(tape_off); cudaFree(tape_chunks); cudaFree(nlev);
   *this = DeviceFactor();
 }
 
 namespace {
 
-constexpr int TRSV_THREADS = 512;
-constexpr int TRSV_NW = TRSV_THREADS / 32;
+constexpr int TRSV_THREADS = 256;
+constexpr int TRSV_NW = TRSV_THREADS / 32;      // warps per CTA
+constexpr int CHW = TAPE_CHUNK_WORDS;           // words per chunk (1 KB)
+constexpr int NCH = 8;                          // chunks per ring (8 KB per warp)
+constexpr int RING_WORDS = NCH * CHW;
+constexpr int TRSV_SMEM = TRSV_NW * (RING_WORDS * 8 + NCH * 8);
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int CL>
 __device__ __forceinline__ void phase_sync() {
@@ -49,134 +52,282 @@ __device__ __forceinline__ void phase_sync() {
   else cg::this_cluster().sync();
 }
 
-// Walks one direction of one agent's schedule.  MODE 0: forward (rhs gathered
-// from V through perm), MODE 1: backward (rhs = forward solution in Y; the
-// result overwrites Y in place and is scattered to OUT through perm).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Per-warp reader of a tape through the shared-memory ring.
+struct TapeReader {
+  const unsigned long long *src;  // this warp's tape (global)
+  unsigned long long *ring;       // RING_WORDS words (shared)
+  uint32_t ring_s, mbar_s;        // shared-space addresses
+  int total;                      // chunks on the tape
+  int issued, ready, freed;       // chunk counters (warp-uniform)
+  int lane;
+
+  __device__ __forceinline__ void issue_one() {
+    // lane 0: arm the slot's mbarrier and start the bulk copy of chunk `issued`
+    const int slot = issued & (NCH - 1);
+    const uint32_t mb = mbar_s + slot * 8;
+    const uint32_t dst = ring_s + slot * (CHW * 8);
+    const unsigned long long *g = src + (size_t)issued * CHW;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(mb), "r"(CHW * 8) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(dst), "l"(g), "r"(CHW * 8), "r"(mb) : "memory");
+  }
+  __device__ __forceinline__ void init(const unsigned long long *tape, int nchunks,
+                                       unsigned long long *ring_, unsigned long long *mbar_,
+                                       int lane_) {
+    src = tape; ring = ring_; total = nchunks; lane = lane_;
+    ring_s = smem_u32(ring_); mbar_s = smem_u32(mbar_);
+    issued = 0; ready = 0; freed = 0;
+    if (lane == 0) {
+      for (int s = 0; s < NCH; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_s + s * 8) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int n0 = total < NCH ? total : NCH;
+    if (lane == 0)
+      for (; issued < n0; ++issued) issue_one();
+    issued = n0;
+  }
+  // make words [.., upto) readable
+  __device__ __forceinline__ void ensure(int upto) {
+    while (ready * CHW < upto) {
+      const uint32_t mb = mbar_s + (ready & (NCH - 1)) * 8;
+      const uint32_t parity = (ready / NCH) & 1;
+      uint32_t ok = 0;
+      do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+      } while (!ok);
+      ++ready;
+    }
+  }
+  // words below `pos` are consumed: recycle their chunks
+  __device__ __forceinline__ void release(int pos) {
+    const int done = pos / CHW;
+    if (freed < done) {
+      __syncwarp();
+      while (freed < done) {
+        if (issued < total) {
+          if (lane == 0) issue_one();
+          ++issued;
+        }
+        ++freed;
+      }
+    }
+  }
+  // wait for every copy still in flight (before the CTA may exit)
+  __device__ __forceinline__ void drain() { ensure(issued * CHW); }
+  __device__ __forceinline__ unsigned long long word(int i) const {
+    return ring[i & (RING_WORDS - 1)];
+  }
+  __device__ __forceinline__ double dword(int i) const {
+    return __longlong_as_double((long long)ring[i & (RING_WORDS - 1)]);
+  }
+};
+
+__device__ __forceinline__ int lo32(unsigned long long u) { return (int)(unsigned)(u & 0xffffffffull); }
+__device__ __forceinline__ int hi32(unsigned long long u) { return (int)(unsigned)(u >> 32); }
+
+// Walks one direction of one agent's tape.  MODE 0: forward (right-hand side
+// gathered from V through the embedded permutation), MODE 1: backward (rhs =
+// forward solution in Y; the result overwrites Y in place and is scattered to
+// OUT through the permutation).
 template <int R, int DH, int CL, int MODE>
-__device__ __forceinline__ void trsv_walk(const DeviceTrsvDir &S, int agent, int gwarp,
-                                          int nwarps, const int *__restrict__ perm,
+__device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
                                           const double *__restrict__ V, double *T,
-                                          double *Y, double *OUT) {
-  const int lane = threadIdx.x & 31;
+                                          double *Y, double *OUT,
+                                          unsigned long long *&trace) {
+  constexpr int BS = DH * DH;
+  constexpr int ITW = 4 + 8 * BS;  // words per phase-A iteration
+  const int lane = rd.lane;
   const int g = lane >> 2, a = lane & 3;
-  const int l0 = S.lvl0[agent], l1 = S.lvl0[agent + 1];
-  for (int lv = l0; lv < l1; ++lv) {
-    const TrsvLevel L = S.levels[lv];
+  for (int lv = 0; lv < nlev; ++lv) {
     // ------------------------------------------------------------ phase A
-    if (L.ta1 > L.ta0) {
-      const int gpt = L.gpt;          // groups per task
-      const int tpw = 8 / gpt;        // tasks per warp
-      const int gg = g & (gpt - 1);   // my group's index within the task
-      for (int base = L.ta0 + gwarp * tpw; base < L.ta1; base += nwarps * tpw) {
-        const int t = base + g / gpt;
-        const bool valid = t < L.ta1;
-        // every lane of the warp takes part in the shuffles below
-        int rr = 0, p0 = 0, p1 = 0;
-        if (valid) { rr = __ldg(S.ta_row + t); p0 = __ldg(S.ta_bptr + t); p1 = __ldg(S.ta_bptr + t + 1); }
-        const bool pose = rr >= 0;
-        const int r0 = pose ? rr : ~rr;
-        double acc[R];
+    rd.ensure(pos + 1);
+    const unsigned long long ah = rd.word(pos);
+    ++pos;
+    const int nrounds = lo32(ah);
+    for (int rnd = 0; rnd < nrounds; ++rnd) {
+      rd.ensure(pos + 17);
+      const unsigned long long rh = rd.word(pos);
+      const int niter = lo32(rh), gpt = hi32(rh);
+      const unsigned long long d0 = rd.word(pos + 1 + 2 * g), d1 = rd.word(pos + 2 + 2 * g);
+      const int r0 = lo32(d0), nrows = hi32(d0), pbase = lo32(d1);
+      pos += 17;
+      // lane (g, a) owns COLUMN a of its group's block: it needs one row of the
+      // source pose (R doubles of Y) per block and accumulates all DH rows of
+      // the product; the 4 lanes of a group are summed once per round.
+      double acc[4][R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) acc[q] = 0.0;
-        const bool rowlane = valid && (pose ? a < DH : a == 0);
-        if (rowlane) {
-          for (int p = p0 + gg; p < p1; p += gpt) {
-            const int c = __ldg(S.bcol + p);
-            const double *qp = S.bval + (size_t)p * (DH * DH) + a * DH;
-            double qv[DH];
-            if constexpr (DH == 4) {
-              const double2 q01 = __ldg(reinterpret_cast<const double2 *>(qp));
-              const double2 q23 = __ldg(reinterpret_cast<const double2 *>(qp) + 1);
-              qv[0] = q01.x; qv[1] = q01.y; qv[2] = q23.x; qv[DH - 1] = q23.y;
-            } else {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-              for (int b = 0; b < DH; ++b) qv[b] = __ldg(qp + b);
-            }
-            const double *yj = Y + (size_t)c * R;
+        for (int q = 0; q < R; ++q) acc[i][q] = 0.0;
+      double yn[R];
 #pragma unroll
-            for (int b = 0; b < DH; ++b) {
+      for (int q = 0; q < R; ++q) yn[q] = 0.0;
+      if (niter > 0) {
+        rd.ensure(pos + ITW);
+        const unsigned long long cw = rd.word(pos + (g >> 1));
+        const int c = (g & 1) ? hi32(cw) : lo32(cw);
+        if (a < DH) {
+          const double *yj = Y + (size_t)(c + a) * R;
 #pragma unroll
-              for (int q = 0; q < R; ++q) acc[q] = fma(qv[b], yj[b * R + q], acc[q]);
-            }
-          }
-          const int s0 = __ldg(S.srowptr + r0 + a), s1 = __ldg(S.srowptr + r0 + a + 1);
-          for (int s = s0 + gg; s < s1; s += gpt) {
-            const double v = __ldg(S.sval + s);
-            const double *yj = Y + (size_t)__ldg(S.scol + s) * R;
-#pragma unroll
-            for (int q = 0; q < R; ++q) acc[q] = fma(v, yj[q], acc[q]);
-          }
-        }
-        for (int o = 4; o < 4 * gpt; o <<= 1) {
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        }
-        if (rowlane && gg == 0) {
-          const size_t o = (size_t)(r0 + a) * R;
-          const double *rhs = MODE == 0 ? V + (size_t)__ldg(perm + r0 + a) * R : Y + o;
-#pragma unroll
-          for (int q = 0; q < R; ++q) T[o + q] = rhs[q] - acc[q];
+          for (int q = 0; q < R; ++q) yn[q] = yj[q];
         }
       }
+      for (int it = 0; it < niter; ++it) {
+        double yc[R], m[DH];
+#pragma unroll
+        for (int q = 0; q < R; ++q) yc[q] = yn[q];
+        if (a < DH) {
+#pragma unroll
+          for (int i = 0; i < DH; ++i) m[i] = rd.dword(pos + 4 + i * (8 * DH) + g * DH + a);
+        } else {
+#pragma unroll
+          for (int i = 0; i < DH; ++i) m[i] = 0.0;
+        }
+        if (it + 1 < niter) {  // gather for the next iteration while this one computes
+          rd.ensure(pos + 2 * ITW);
+          const unsigned long long cw = rd.word(pos + ITW + (g >> 1));
+          const int c = (g & 1) ? hi32(cw) : lo32(cw);
+          if (a < DH) {
+            const double *yj = Y + (size_t)(c + a) * R;
+#pragma unroll
+            for (int q = 0; q < R; ++q) yn[q] = yj[q];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < DH; ++i)
+#pragma unroll
+          for (int q = 0; q < R; ++q) acc[i][q] = fma(m[i], yc[q], acc[i][q]);
+        pos += ITW;
+        rd.release(pos);
+      }
+      // sum over the 4 lanes of the group, leaving row a in lane a
+      double row[R];
+      {
+        double v[2][R];
+        const bool hi2 = (a & 2) != 0, hi1 = (a & 1) != 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const double mine = hi2 ? acc[2 + h][q] : acc[h][q];
+            const double send = hi2 ? acc[h][q] : acc[2 + h][q];
+            v[h][q] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const double mine = hi1 ? v[1][q] : v[0][q];
+          const double send = hi1 ? v[0][q] : v[1][q];
+          row[q] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+      }
+      for (int o = 4; o < 4 * gpt; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) row[q] += __shfl_xor_sync(0xffffffffu, row[q], o);
+      }
+      if (r0 >= 0 && a < nrows && (g & (gpt - 1)) == 0) {
+        const size_t o = (size_t)(r0 + a) * R;
+        const double *rhs = MODE == 0 ? V + (size_t)(pbase + a) * R : Y + o;
+#pragma unroll
+        for (int q = 0; q < R; ++q) T[o + q] = rhs[q] - row[q];
+      }
+      rd.release(pos);
+    }
+    if (hi32(ah) != 0) {  // the level has a phase A (agent-uniform)
       phase_sync<CL>();
+      if (trace) *trace++ = globaltimer_ns() | 1ull;  // odd: end of a phase A
     }
     // ------------------------------------------------------------ phase B
-    // small blocks: one warp per block, lane = row, matrix packed by columns
-    for (int s = L.sb0 + gwarp; s < L.sb1; s += nwarps) {
-      const int r0 = __ldg(S.sb_row0 + s), w = __ldg(S.sb_w + s);
-      const double *M = S.dense + __ldg(S.sb_off + s);
-      const bool direct = MODE == 0 && __ldg(S.sb_direct + s) != 0;
+    rd.ensure(pos + 1);
+    const unsigned long long bh = rd.word(pos);
+    ++pos;
+    const int nsmall = lo32(bh), nlarge = hi32(bh);
+    // small blocks: lane = row, packed triangle consumed column by column
+    for (int s = 0; s < nsmall; ++s) {
+      rd.ensure(pos + 2);
+      const unsigned long long h0 = rd.word(pos), h1 = rd.word(pos + 1);
+      const int r0 = lo32(h0), w = hi32(h0);
+      const bool direct = MODE == 0 && lo32(h1) != 0;
+      pos += 2;
+      const int npw = (w + 1) >> 1;
+      rd.ensure(pos + npw);
+      int pm = 0;
+      if (lane < w) {
+        const unsigned long long pw = rd.word(pos + (lane >> 1));
+        pm = (lane & 1) ? hi32(pw) : lo32(pw);
+      }
+      pos += npw;
       double tv[R], acc[R];
 #pragma unroll
       for (int q = 0; q < R; ++q) { tv[q] = 0.0; acc[q] = 0.0; }
       if (lane < w) {
-        const double *src = direct ? V + (size_t)__ldg(perm + r0 + lane) * R
-                                   : T + (size_t)(r0 + lane) * R;
+        const double *src = direct ? V + (size_t)pm * R : T + (size_t)(r0 + lane) * R;
 #pragma unroll
         for (int q = 0; q < R; ++q) tv[q] = src[q];
       }
-      int off = 0;
-      for (int j = 0; j < w; ++j) {
-        double m = 0.0;
-        if (MODE == 0) {            // column j holds rows j..w-1
-          if (lane >= j && lane < w) m = __ldg(M + off + (lane - j));
-          off += w - j;
-        } else {                    // column j holds rows 0..j
-          if (lane <= j) m = __ldg(M + off + lane);
-          off += j + 1;
-        }
+      rd.ensure(pos + w * (w + 1) / 2);  // the whole packed triangle (<= 528 words)
+      {
+        int off = pos;
+#pragma unroll 4
+        for (int j = 0; j < w; ++j) {
+          double m = 0.0;
+          if (MODE == 0) {            // column j holds rows j..w-1
+            if (lane >= j && lane < w) m = rd.dword(off + (lane - j));
+            off += w - j;
+          } else {                    // column j holds rows 0..j
+            if (lane <= j) m = rd.dword(off + lane);
+            off += j + 1;
+          }
 #pragma unroll
-        for (int q = 0; q < R; ++q) acc[q] = fma(m, __shfl_sync(0xffffffffu, tv[q], j), acc[q]);
+          for (int q = 0; q < R; ++q) acc[q] = fma(m, __shfl_sync(0xffffffffu, tv[q], j), acc[q]);
+        }
+        pos = off;
       }
+      rd.release(pos);
       if (lane < w) {
         const size_t o = (size_t)(r0 + lane) * R;
 #pragma unroll
         for (int q = 0; q < R; ++q) Y[o + q] = acc[q];
         if (MODE == 1) {
-          const size_t oo = (size_t)__ldg(perm + r0 + lane) * R;
+          const size_t oo = (size_t)pm * R;
 #pragma unroll
           for (int q = 0; q < R; ++q) OUT[oo + q] = acc[q];
         }
       }
     }
-    // rows of large blocks: one warp per row, matrix packed by rows
-    for (int t = L.lr0 + gwarp; t < L.lr1; t += nwarps) {
-      const int lb = __ldg(S.lr_blk + t), i = __ldg(S.lr_i + t);
-      const int r0 = __ldg(S.lb_row0 + lb), w = __ldg(S.lb_w + lb);
-      const bool direct = MODE == 0 && __ldg(S.lb_direct + lb) != 0;
-      const double *M = S.dense + __ldg(S.lb_off + lb);
-      int j0, j1;
-      if (MODE == 0) { M += (int64_t)i * (i + 1) / 2; j0 = 0; j1 = i + 1; }
-      else { M += (int64_t)i * w - (int64_t)i * (i - 1) / 2; j0 = i; j1 = w; }
+    // rows of large blocks: lanes stride along the row
+    for (int l = 0; l < nlarge; ++l) {
+      rd.ensure(pos + 2);
+      const unsigned long long h0 = rd.word(pos), h1 = rd.word(pos + 1);
+      const int src0 = lo32(h0), len = hi32(h0);
+      const int dest = lo32(h1), dperm = hi32(h1);
+      pos += 2;
       double acc[R];
 #pragma unroll
       for (int q = 0; q < R; ++q) acc[q] = 0.0;
-      for (int j = j0 + lane; j < j1; j += 32) {
-        const double m = __ldg(M + (j - j0));
-        const double *src = direct ? V + (size_t)__ldg(perm + r0 + j) * R
-                                   : T + (size_t)(r0 + j) * R;
+      const double *srcp = T + (size_t)src0 * R;
+      for (int j0 = 0; j0 < len; j0 += CHW) {
+        const int n = len - j0 < CHW ? len - j0 : CHW;
+        rd.ensure(pos + n);
+#pragma unroll 4
+        for (int j = lane; j < n; j += 32) {
+          const double m = rd.dword(pos + j);
+          const double *sv = srcp + (size_t)(j0 + j) * R;
 #pragma unroll
-        for (int q = 0; q < R; ++q) acc[q] = fma(m, src[q], acc[q]);
+          for (int q = 0; q < R; ++q) acc[q] = fma(m, sv[q], acc[q]);
+        }
+        pos += n;
+        rd.release(pos);
       }
 #pragma unroll
       for (int q = 0; q < R; ++q) {
@@ -188,26 +339,44 @@ __device__ __forceinline__ void trsv_walk(const DeviceTrsvDir &S, int agent, int
 #pragma unroll
         for (int q = 0; q < R; ++q)
           if (q == lane) sres = acc[q];
-        Y[(size_t)(r0 + i) * R + lane] = sres;
-        if (MODE == 1) OUT[(size_t)__ldg(perm + r0 + i) * R + lane] = sres;
+        Y[(size_t)dest * R + lane] = sres;
+        if (MODE == 1) OUT[(size_t)dperm * R + lane] = sres;
       }
     }
     phase_sync<CL>();
+    if (trace) *trace++ = globaltimer_ns() & ~1ull;  // even: end of a phase B
   }
 }
 
 template <int R, int DH, int CL>
 __global__ void __launch_bounds__(TRSV_THREADS)
-trsv_block_kernel(const int *__restrict__ flags, int mask_flag, DeviceTrsvDir fwd,
-                  DeviceTrsvDir bwd, const int *__restrict__ perm,
-                  const double *__restrict__ V, double *T, double *Y, double *OUT) {
+trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
+                 const unsigned long long *__restrict__ tape,
+                 const long long *__restrict__ tape_off, const int *__restrict__ tape_chunks,
+                 const int *__restrict__ nlev, const double *__restrict__ V, double *T,
+                 double *Y, double *OUT, unsigned long long *trace_buf, int trace_agent) {
   const int agent = blockIdx.x / CL;
   if (mask_flag >= 0 && flags[agent * NF + mask_flag] == 0) return;  // whole cluster
   const int crank = blockIdx.x - agent * CL;
-  const int gwarp = crank * TRSV_NW + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = crank * TRSV_NW + warp;
   constexpr int nwarps = CL * TRSV_NW;
-  trsv_walk<R, DH, CL, 0>(fwd, agent, gwarp, nwarps, perm, V, T, Y, OUT);
-  trsv_walk<R, DH, CL, 1>(bwd, agent, gwarp, nwarps, perm, V, T, Y, OUT);
+  extern __shared__ __align__(128) unsigned long long trsv_smem[];
+  unsigned long long *ring = trsv_smem + warp * RING_WORDS;
+  unsigned long long *mbar = trsv_smem + TRSV_NW * RING_WORDS + warp * NCH;
+  const size_t wi = (size_t)agent * nwarps + gwarp;
+  TapeReader rd;
+  rd.init(tape + tape_off[wi], tape_chunks[wi], ring, mbar, lane);
+  // optional phase trace (debug / profiling aid): thread 0 of the traced
+  // agent's first CTA stamps the end of every phase
+  unsigned long long *trace =
+      (trace_buf && agent == trace_agent && gwarp == 0 && lane == 0) ? trace_buf : nullptr;
+  if (trace) *trace++ = globaltimer_ns();
+  int pos = 0;
+  trsv_walk<R, DH, CL, 0>(rd, pos, nlev[agent * 2 + 0], V, T, Y, OUT, trace);
+  trsv_walk<R, DH, CL, 1>(rd, pos, nlev[agent * 2 + 1], V, T, Y, OUT, trace);
+  if (trace) *trace = 0ull;
+  rd.drain();
 }
 
 template <typename T>
@@ -218,113 +387,77 @@ cudaError_t up(T **dst, const std::vector<T> &src) {
   return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
-template <typename T>
-void append_shift(std::vector<T> &dst, const std::vector<T> &src, T shift) {
-  const size_t n0 = dst.size();
-  dst.resize(n0 + src.size());
-  for (size_t i = 0; i < src.size(); ++i) dst[n0 + i] = src[i] + shift;
-}
-
 }  // namespace
 
+int trsv_cluster_for(double rows_per_agent) {
+  // enough CTAs to spread one agent's factor over several SMs; a single CTA
+  // for tiny agents (the level barriers become __syncthreads)
+  return rows_per_agent < 400.0 ? 1 : rows_per_agent < 1500.0 ? 2
+         : rows_per_agent < 4000.0 ? 4 : 8;
+}
+int trsv_warps_per_cta() { return TRSV_NW; }
+
 int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
-                  std::vector<AgentTrsv> &AT, const HostLayout &H) {
+                  std::vector<AgentTape> &AT, int cluster, const HostLayout &H) {
   DeviceFactor &F = M->F;
   const int A = H.A;
-  const int64_t K = H.K;
-  int64_t nnzL = 0;
-  for (int a = 0; a < A; ++a) nnzL += HF[a].nnz;
-  std::vector<int> perm(K);
-  for (int a = 0; a < A; ++a)
-    for (int j = 0; j < HF[a].k; ++j) perm[H.coff[a] + j] = (int)H.coff[a] + HF[a].perm[j];
-  DCORA_CUDA(up(&F.perm, perm));
-  int64_t stored = 0;
+  const int nwarps = cluster * TRSV_NW;
+  int64_t nnzL = 0, stored = 0, words = 0;
   int max_levels = 0;
-  for (int d = 0; d < 2; ++d) {
-    // concatenate the agents' schedules with global row / array offsets
-    std::vector<int> ta_row, ta_bptr(1, 0), bcol, srowptr(1, 0), scol;
-    std::vector<double> bval, sval, dense;
-    std::vector<int> sb_row0, sb_w, sb_direct, lb_row0, lb_w, lb_direct, lr_blk, lr_i;
-    std::vector<long long> sb_off, lb_off;
-    std::vector<TrsvLevel> levels;
-    std::vector<int> lvl0(A + 1, 0);
-    for (int a = 0; a < A; ++a) {
-      AgentTrsvDir &S = AT[a].dir[d];
-      const int c0 = (int)H.coff[a];
-      if ((int64_t)bcol.size() + (int64_t)S.bcol.size() >= ((int64_t)1 << 31) / 16 * 16 ||
-          (int64_t)scol.size() + (int64_t)S.scol.size() >= ((int64_t)1 << 31)) {
-        set_error("upload_factor: factor too large for int32 indexing");
-        return DCORA_ERR_ARG;
-      }
-      const int t0 = (int)ta_row.size(), b0 = (int)bcol.size(), s0 = (int)scol.size();
-      const int sb0 = (int)sb_row0.size(), lb0 = (int)lb_row0.size(), lr0 = (int)lr_blk.size();
-      const int64_t d0 = (int64_t)dense.size();
-      for (int v : S.ta_row) ta_row.push_back(v >= 0 ? v + c0 : ~((~v) + c0));
-      for (size_t i = 1; i < S.ta_bptr.size(); ++i) ta_bptr.push_back(S.ta_bptr[i] + b0);
-      append_shift(bcol, S.bcol, c0);
-      bval.insert(bval.end(), S.bval.begin(), S.bval.end());
-      for (size_t i = 1; i < S.srowptr.size(); ++i) srowptr.push_back(S.srowptr[i] + s0);
-      append_shift(scol, S.scol, c0);
-      sval.insert(sval.end(), S.sval.begin(), S.sval.end());
-      append_shift(sb_row0, S.sb_row0, c0);
-      sb_w.insert(sb_w.end(), S.sb_w.begin(), S.sb_w.end());
-      sb_direct.insert(sb_direct.end(), S.sb_direct.begin(), S.sb_direct.end());
-      for (int64_t v : S.sb_off) sb_off.push_back((long long)(v + d0));
-      append_shift(lb_row0, S.lb_row0, c0);
-      lb_w.insert(lb_w.end(), S.lb_w.begin(), S.lb_w.end());
-      lb_direct.insert(lb_direct.end(), S.lb_direct.begin(), S.lb_direct.end());
-      for (int64_t v : S.lb_off) lb_off.push_back((long long)(v + d0));
-      append_shift(lr_blk, S.lr_blk, lb0);
-      lr_i.insert(lr_i.end(), S.lr_i.begin(), S.lr_i.end());
-      dense.insert(dense.end(), S.dense.begin(), S.dense.end());
-      for (TrsvLevel L : S.levels) {
-        L.ta0 += t0; L.ta1 += t0; L.sb0 += sb0; L.sb1 += sb0; L.lr0 += lr0; L.lr1 += lr0;
-        levels.push_back(L);
-      }
-      lvl0[a + 1] = (int)levels.size();
-      max_levels = std::max(max_levels, (int)S.levels.size());
-      S = AgentTrsvDir();  // release host memory early
-    }
-    if ((int64_t)srowptr.size() != K + 1) {
-      set_error("upload_factor: inconsistent schedule");
+  std::vector<long long> off((size_t)A * nwarps);
+  std::vector<int> chunks((size_t)A * nwarps), nlev((size_t)A * 2);
+  for (int a = 0; a < A; ++a) {
+    nnzL += HF[a].nnz;
+    stored += AT[a].stored_values;
+    if (AT[a].nwarps != nwarps) {
+      set_error("upload_factor: tape built for another cluster size");
       return DCORA_ERR_ARG;
     }
-    stored += (int64_t)bval.size() + (int64_t)sval.size() + (int64_t)dense.size();
-    DeviceTrsvDir &T = F.dir[d];
-    DCORA_CUDA(up(&T.ta_row, ta_row));   DCORA_CUDA(up(&T.ta_bptr, ta_bptr));
-    DCORA_CUDA(up(&T.bcol, bcol));       DCORA_CUDA(up(&T.bval, bval));
-    DCORA_CUDA(up(&T.srowptr, srowptr)); DCORA_CUDA(up(&T.scol, scol));
-    DCORA_CUDA(up(&T.sval, sval));
-    DCORA_CUDA(up(&T.sb_row0, sb_row0)); DCORA_CUDA(up(&T.sb_w, sb_w));
-    DCORA_CUDA(up(&T.sb_direct, sb_direct)); DCORA_CUDA(up(&T.sb_off, sb_off));
-    DCORA_CUDA(up(&T.lb_row0, lb_row0)); DCORA_CUDA(up(&T.lb_w, lb_w));
-    DCORA_CUDA(up(&T.lb_direct, lb_direct)); DCORA_CUDA(up(&T.lb_off, lb_off));
-    DCORA_CUDA(up(&T.lr_blk, lr_blk));   DCORA_CUDA(up(&T.lr_i, lr_i));
-    DCORA_CUDA(up(&T.dense, dense));
-    DCORA_CUDA(up(&T.levels, levels));   DCORA_CUDA(up(&T.lvl0, lvl0));
+    for (int w = 0; w < nwarps; ++w) {
+      off[(size_t)a * nwarps + w] = words;
+      chunks[(size_t)a * nwarps + w] = (int)(AT[a].warp_tape[w].size() / TAPE_CHUNK_WORDS);
+      words += (int64_t)AT[a].warp_tape[w].size();
+    }
+    nlev[a * 2 + 0] = AT[a].nlev[0];
+    nlev[a * 2 + 1] = AT[a].nlev[1];
+    max_levels = std::max(max_levels, std::max(AT[a].nlev[0], AT[a].nlev[1]));
   }
+  DCORA_CUDA(cudaMalloc(&F.tape, std::max<int64_t>(1, words) * sizeof(unsigned long long)));
+  for (int a = 0; a < A; ++a) {
+    for (int w = 0; w < nwarps; ++w) {
+      const std::vector<uint64_t> &tp = AT[a].warp_tape[w];
+      if (!tp.empty())
+        DCORA_CUDA(cudaMemcpy(F.tape + off[(size_t)a * nwarps + w], tp.data(),
+                              tp.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    AT[a] = AgentTape();  // release host memory early
+  }
+  DCORA_CUDA(up(&F.tape_off, off));
+  DCORA_CUDA(up(&F.tape_chunks, chunks));
+  DCORA_CUDA(up(&F.nlev, nlev));
   F.present = true;
   F.nnzL = nnzL;
   F.stored_values = stored / 2;
+  F.tape_bytes = words * 8;
   F.A = A;
   F.max_levels = max_levels;
-  // cluster size: enough CTAs to spread one agent's factor over several SMs,
-  // a single CTA for tiny agents (level barriers become __syncthreads)
-  const double per_agent = (double)nnzL / std::max(1, A);
-  F.cluster = per_agent < 2.0e4 ? 1 : per_agent < 1.0e5 ? 2 : per_agent < 4.0e5 ? 4 : 8;
+  F.cluster = cluster;
   return DCORA_OK;
 }
 
 template <int R, int DH, int CL>
 static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
-                       double *OUT, int mask_flag) {
+                       double *OUT, int mask_flag, unsigned long long *trace,
+                       int trace_agent) {
   DeviceMatrices &M = *p->M;
   const DeviceFactor &F = M.F;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(M.A * CL));
   cfg.blockDim = dim3(TRSV_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = TRSV_SMEM;
   cfg.stream = p->stream;
+  DCORA_CUDA(cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
@@ -332,15 +465,16 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  DCORA_CUDA(cudaLaunchKernelEx(&cfg, trsv_block_kernel<R, DH, CL>,
-                                (const int *)p->flags, mask_flag, F.dir[0], F.dir[1],
-                                (const int *)F.perm, V, T, Y, OUT));
+  DCORA_CUDA(cudaLaunchKernelEx(&cfg, trsv_tape_kernel<R, DH, CL>, (const int *)p->flags,
+                                mask_flag, (const unsigned long long *)F.tape,
+                                (const long long *)F.tape_off, (const int *)F.tape_chunks,
+                                (const int *)F.nlev, V, T, Y, OUT, trace, trace_agent));
   p->launches++;
   return DCORA_OK;
 }
 
 int launch_precond(dcora_problem *p, const double *X, const double *V, double *OUT,
-                   int mask_flag) {
+                   int mask_flag, unsigned long long *trace, int trace_agent) {
   DeviceMatrices &M = *p->M;
   const DeviceFactor &F = M.F;
   if (!F.present) {
@@ -354,10 +488,10 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
   if (!panel || !sol || !tmp) return DCORA_ERR_ALLOC;
   DCORA_DISPATCH_RD(p->r, M.d, {
     switch (F.cluster) {
-      case 1: DCORA_TRY((launch_trsv<R, DH, 1>(p, V, tmp, panel, sol, mask_flag))); break;
-      case 2: DCORA_TRY((launch_trsv<R, DH, 2>(p, V, tmp, panel, sol, mask_flag))); break;
-      case 4: DCORA_TRY((launch_trsv<R, DH, 4>(p, V, tmp, panel, sol, mask_flag))); break;
-      default: DCORA_TRY((launch_trsv<R, DH, 8>(p, V, tmp, panel, sol, mask_flag))); break;
+      case 1: DCORA_TRY((launch_trsv<R, DH, 1>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
+      case 2: DCORA_TRY((launch_trsv<R, DH, 2>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
+      case 4: DCORA_TRY((launch_trsv<R, DH, 4>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
+      default: DCORA_TRY((launch_trsv<R, DH, 8>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
     }
   })
   return launch_project_tangent(p, X, sol, OUT, mask_flag);

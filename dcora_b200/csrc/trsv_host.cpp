@@ -1,7 +1,7 @@
-// Host-side construction of the BLOCK triangular-solve schedule (K5).
+// Host-side construction of the BLOCK triangular-solve tapes (K5).
 //
-// The reference applies its preconditioner with CHOLMOD's
-// solve (src/QuadraticProblem.cpp:79, src/Graph.cpp:1901-1917).  A scalar,
+// The reference applies its preconditioner with CHOLMOD's solve
+// (src/QuadraticProblem.cpp:79, src/Graph.cpp:1901-1917).  A scalar,
 // level-scheduled SpTRSV has a critical path of thousands of dependent rows
 // per agent, which a GPU cannot hide.  Here the factor L (chol.cpp, nested-
 // dissection ordering) is regrouped by the ND blocks B_1..B_m (leaf
@@ -10,17 +10,18 @@
 //   forward   y_B = D_B ( b_B - L[B, <B] y )          D_B = inv(L[B, B])
 //   backward  x_B = D_B^T ( y_B - L[>B, B]^T x )
 //
-// so a block costs one sparse "phase A" (off-diagonal rows, a small SpMM
-// against the already solved part) and one dense "phase B" (a triangular
-// matrix-vector product with the explicitly inverted diagonal block); blocks
-// of one level of the block elimination tree are independent and the tree is
-// only O(log n) levels deep.  Off-diagonal entries that couple two pose
-// supervariables are stored as dense (d+1)x(d+1) blocks (one index per 128 B,
-// like Q itself), everything else (unit-sphere / landmark rows and columns)
-// as scalar CSR.
+// so a block costs one sparse "phase A" (off-diagonal rows against the already
+// solved part, stored as dense (d+1)x(d+1) blocks) and one dense "phase B" (a
+// triangular matrix-vector product with the explicitly inverted diagonal
+// block); blocks of one level of the block elimination tree are independent
+// and the tree is only O(log n) levels deep.  The work of every phase is dealt
+// to the warps of the agent's cluster here, on the host, and written out as
+// one tape per warp (format: trsv.h).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <numeric>
+#include <queue>
 
 #include "trsv.h"
 
@@ -32,6 +33,22 @@ struct Csr {
   std::vector<int> ptr, col;
   std::vector<double> val;
 };
+
+inline uint64_t pack2(int lo, int hi) {
+  return (uint64_t)(uint32_t)lo | ((uint64_t)(uint32_t)hi << 32);
+}
+inline uint64_t dbits(double v) {
+  uint64_t u;
+  std::memcpy(&u, &v, 8);
+  return u;
+}
+inline double bitsd(uint64_t u) {
+  double v;
+  std::memcpy(&v, &u, 8);
+  return v;
+}
+inline int lo32(uint64_t u) { return (int)(uint32_t)(u & 0xffffffffu); }
+inline int hi32(uint64_t u) { return (int)(uint32_t)(u >> 32); }
 
 // inverse of the lower-triangular diagonal block rows [s, e) of L (CSC)
 void invert_diag_block(const HostFactor &F, int s, int e, std::vector<double> *Dout) {
@@ -56,10 +73,37 @@ void invert_diag_block(const HostFactor &F, int s, int e, std::vector<double> *D
   }
 }
 
+struct ATask {
+  int r0, nrows;
+  std::vector<int> src;        // source row starts, sorted
+  std::vector<double> val;     // dh*dh per source, [a][b]
+  int gpt = 1;
+};
+
+struct Round {
+  int gpt, niter;
+  std::vector<int> tasks;      // indices into the level's task list (<= 8/gpt)
+};
+
+// longest-processing-time assignment: items sorted by decreasing cost
+struct Lpt {
+  typedef std::pair<int64_t, int> LI;
+  std::priority_queue<LI, std::vector<LI>, std::greater<LI>> pq;
+  explicit Lpt(int nw) { for (int w = 0; w < nw; ++w) pq.push(LI(0, w)); }
+  int take(int64_t cost) {
+    LI t = pq.top();
+    pq.pop();
+    pq.push(LI(t.first + cost, t.second));
+    return t.second;
+  }
+};
+
 }  // namespace
 
-int build_agent_trsv(const HostFactor &F, int dh, AgentTrsv *out) {
+int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, int row_offset,
+                     AgentTape *out) {
   const int k = F.k;
+  const int bs = dh * dh;
   // ---- final block partition: ND blocks, split to at most TRSV_MAX_BLOCK rows
   std::vector<int> bp(1, 0);
   for (size_t b = 0; b + 1 < F.blk_ptr.size(); ++b) {
@@ -113,8 +157,20 @@ int build_agent_trsv(const HostFactor &F, int dh, AgentTrsv *out) {
 
   out->k = k;
   out->nblocks = nb;
+  out->nwarps = nwarps_total;
+  out->dh = dh;
+  out->warp_tape.assign(nwarps_total, std::vector<uint64_t>());
+  out->stored_values = 0;
+  const int R0 = row_offset;
+  // first row of the (d+1)-row window a source column is read through: its pose
+  // block, or -- for a unit-sphere / landmark row -- a window that stays inside
+  // the agent's own rows (the other rows of the window meet zeros)
+  auto src_start = [&](int c) {
+    if (F.pose_start[c] >= 0) return F.pose_start[c];
+    return std::max(0, std::min(c, k - dh));
+  };
+
   for (int dir = 0; dir < 2; ++dir) {
-    AgentTrsvDir &T = out->dir[dir];
     const Csr &A = M[dir];
     // levels of the block DAG
     std::vector<int> lvl(nb, 0);
@@ -127,174 +183,279 @@ int build_agent_trsv(const HostFactor &F, int dh, AgentTrsv *out) {
       lvl[b] = lv;
       nlev = std::max(nlev, lv + 1);
     }
+    out->nlev[dir] = nlev;
     std::vector<std::vector<int>> by_level(nlev);
     for (int b = 0; b < nb; ++b) by_level[lvl[b]].push_back(b);
 
-    T.srowptr.assign(k + 1, 0);
-    T.ta_bptr.assign(1, 0);
-    std::vector<int> scnt(k, 0);
-    std::vector<int> mark(k, -1);
     for (int lv = 0; lv < nlev; ++lv) {
-      TrsvLevel L;
-      L.ta0 = (int)T.ta_row.size();
-      L.sb0 = (int)T.sb_row0.size();
-      L.lr0 = (int)T.lr_blk.size();
-      int64_t nblk_level = 0, npose_tasks = 0;
-      for (int b : by_level[lv]) {
-        const int s = bp[b], e = bp[b + 1], w = e - s;
+      // ------------------------------------------------ phase A tasks
+      std::vector<ATask> tasks;
+      std::vector<int> direct_of(by_level[lv].size(), 0);
+      int64_t total_blocks = 0;
+      for (size_t bi = 0; bi < by_level[lv].size(); ++bi) {
+        const int b = by_level[lv][bi];
+        const int s = bp[b], e = bp[b + 1];
         bool has = false;
         for (int r = s; r < e && !has; ++r) has = A.ptr[r + 1] > A.ptr[r];
-        const int direct = (dir == 0 && !has) ? 1 : 0;
-        if (!direct) {
-          for (int r = s; r < e;) {
-            if (F.pose_start[r] == r) {
-              // pose task: union of the source pose blocks over the dh rows
-              std::vector<int> cols;
-              for (int a = 0; a < dh; ++a)
-                for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
-                  const int ps = F.pose_start[A.col[p]];
-                  if (ps >= 0) {
-                    if (mark[ps] != r) { mark[ps] = r; cols.push_back(ps); }
-                  } else {
-                    scnt[r + a]++;
-                  }
-                }
-              std::sort(cols.begin(), cols.end());
-              const size_t base = T.bcol.size();
-              T.bcol.insert(T.bcol.end(), cols.begin(), cols.end());
-              T.bval.resize(T.bcol.size() * (size_t)dh * dh, 0.0);
-              for (int a = 0; a < dh; ++a)
-                for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
-                  const int c = A.col[p], ps = F.pose_start[c];
-                  if (ps < 0) continue;
-                  const size_t q = base + (std::lower_bound(cols.begin(), cols.end(), ps) - cols.begin());
-                  T.bval[q * dh * dh + (size_t)a * dh + (c - ps)] = A.val[p];
-                }
-              T.ta_row.push_back(r);
-              T.ta_bptr.push_back((int)T.bcol.size());
-              nblk_level += (int64_t)cols.size();
-              ++npose_tasks;
-              r += dh;
+        // only small forward blocks without predecessors read their right-hand
+        // side directly (through perm); everything else gets a phase-A task
+        const int direct = (dir == 0 && !has && e - s <= TRSV_SMALL_BLOCK) ? 1 : 0;
+        direct_of[bi] = direct;
+        if (direct) continue;
+        for (int r = s; r < e;) {
+          ATask tk;
+          tk.r0 = r;
+          tk.nrows = F.pose_start[r] == r ? dh : 1;
+          // sources: pose blocks (start row ps) or single scalar rows (b = 0)
+          for (int a = 0; a < tk.nrows; ++a)
+            for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
+              tk.src.push_back(src_start(A.col[p]));
+            }
+          std::sort(tk.src.begin(), tk.src.end());
+          tk.src.erase(std::unique(tk.src.begin(), tk.src.end()), tk.src.end());
+          tk.val.assign(tk.src.size() * (size_t)bs, 0.0);
+          for (int a = 0; a < tk.nrows; ++a)
+            for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
+              const int c = A.col[p];
+              const int ps = src_start(c);
+              const size_t q = std::lower_bound(tk.src.begin(), tk.src.end(), ps) - tk.src.begin();
+              tk.val[q * bs + (size_t)a * dh + (c - ps)] = A.val[p];
+            }
+          total_blocks += (int64_t)tk.src.size();
+          r += tk.nrows;
+          tasks.push_back(std::move(tk));
+        }
+      }
+      const bool a_present = !tasks.empty();
+      // groups per task: split tasks that are long compared with the ideal
+      // per-group load of the level
+      const int64_t target = std::max<int64_t>(2, (total_blocks + (int64_t)nwarps * 8 - 1) / ((int64_t)nwarps * 8));
+      for (ATask &tk : tasks) {
+        int g = 1;
+        while (g < 8 && (int64_t)tk.src.size() > target * g) g *= 2;
+        tk.gpt = g;
+      }
+      std::vector<int> ord(tasks.size());
+      std::iota(ord.begin(), ord.end(), 0);
+      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+        if (tasks[x].gpt != tasks[y].gpt) return tasks[x].gpt > tasks[y].gpt;
+        return tasks[x].src.size() > tasks[y].src.size();
+      });
+      std::vector<Round> rounds;
+      for (size_t i = 0; i < ord.size();) {
+        Round rd;
+        rd.gpt = tasks[ord[i]].gpt;
+        rd.niter = 0;
+        const int tpw = 8 / rd.gpt;
+        while (i < ord.size() && (int)rd.tasks.size() < tpw && tasks[ord[i]].gpt == rd.gpt) {
+          const int nbk = (int)tasks[ord[i]].src.size();
+          rd.niter = std::max(rd.niter, (nbk + rd.gpt - 1) / rd.gpt);
+          rd.tasks.push_back(ord[i]);
+          ++i;
+        }
+        rounds.push_back(std::move(rd));
+      }
+      std::stable_sort(rounds.begin(), rounds.end(),
+                       [](const Round &x, const Round &y) { return x.niter > y.niter; });
+      std::vector<std::vector<int>> warp_rounds(nwarps);
+      {
+        Lpt lpt(nwarps);
+        for (size_t i = 0; i < rounds.size(); ++i)
+          warp_rounds[lpt.take(rounds[i].niter + 2)].push_back((int)i);
+      }
+      // ------------------------------------------------ phase B items
+      struct Small { int b, direct; };
+      struct Large { int b, i, len; };
+      std::vector<Small> smalls;
+      std::vector<Large> larges;
+      for (size_t bi = 0; bi < by_level[lv].size(); ++bi) {
+        const int b = by_level[lv][bi];
+        const int w = bp[b + 1] - bp[b];
+        if (w <= TRSV_SMALL_BLOCK) smalls.push_back({b, direct_of[bi]});
+        else for (int i = 0; i < w; ++i) larges.push_back({b, i, dir == 0 ? i + 1 : w - i});
+      }
+      std::stable_sort(smalls.begin(), smalls.end(), [&](const Small &x, const Small &y) {
+        return bp[x.b + 1] - bp[x.b] > bp[y.b + 1] - bp[y.b];
+      });
+      std::stable_sort(larges.begin(), larges.end(),
+                       [](const Large &x, const Large &y) { return x.len > y.len; });
+      std::vector<std::vector<int>> warp_small(nwarps), warp_large(nwarps);
+      {
+        Lpt lpt(nwarps);
+        for (size_t i = 0; i < smalls.size(); ++i)
+          warp_small[lpt.take(bp[smalls[i].b + 1] - bp[smalls[i].b] + 16)].push_back((int)i);
+        for (size_t i = 0; i < larges.size(); ++i)
+          warp_large[lpt.take(larges[i].len / 16 + 8)].push_back((int)i);
+      }
+      // ------------------------------------------------ emit
+      for (int wi = 0; wi < nwarps; ++wi) {
+        std::vector<uint64_t> &tp = out->warp_tape[wi];
+        tp.push_back(pack2((int)warp_rounds[wi].size(), a_present ? 1 : 0));
+        for (int ri : warp_rounds[wi]) {
+          const Round &rd = rounds[ri];
+          tp.push_back(pack2(rd.niter, rd.gpt));
+          for (int g = 0; g < 8; ++g) {
+            const int ti = g / rd.gpt;
+            if (ti < (int)rd.tasks.size()) {
+              const ATask &tk = tasks[rd.tasks[ti]];
+              tp.push_back(pack2(R0 + tk.r0, tk.nrows));
+              tp.push_back(pack2(R0 + F.perm[tk.r0], 0));
             } else {
-              scnt[r] += A.ptr[r + 1] - A.ptr[r];
-              T.ta_row.push_back(~r);
-              T.ta_bptr.push_back((int)T.bcol.size());
-              r += 1;
+              tp.push_back(pack2(-1, 0));
+              tp.push_back(pack2(0, 0));
             }
           }
+          for (int it = 0; it < rd.niter; ++it) {
+            int c[8];
+            const double *vp[8];
+            for (int g = 0; g < 8; ++g) {
+              const int ti = g / rd.gpt, gg = g % rd.gpt;
+              c[g] = R0;  // padding: any valid row, zero block
+              vp[g] = nullptr;
+              if (ti < (int)rd.tasks.size()) {
+                const ATask &tk = tasks[rd.tasks[ti]];
+                const int q = it * rd.gpt + gg;
+                if (q < (int)tk.src.size()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
+              }
+            }
+            for (int g = 0; g < 8; g += 2) tp.push_back(pack2(c[g], c[g + 1]));
+            // block row a of all 8 groups together: the 32 lanes (group, column)
+            // of a warp read 32 consecutive words (no shared-memory bank conflict)
+            for (int a = 0; a < dh; ++a)
+              for (int g = 0; g < 8; ++g)
+                for (int bb = 0; bb < dh; ++bb)
+                  tp.push_back(dbits(vp[g] ? vp[g][a * dh + bb] : 0.0));
+            out->stored_values += 8 * bs;
+          }
         }
-        // phase B
-        const std::vector<double> &D = Dinv[b];
-        const int64_t off = (int64_t)T.dense.size();
-        if (w <= TRSV_SMALL_BLOCK) {
+        tp.push_back(pack2((int)warp_small[wi].size(), (int)warp_large[wi].size()));
+        for (int si : warp_small[wi]) {
+          const int b = smalls[si].b, s = bp[b], w = bp[b + 1] - s;
+          const std::vector<double> &D = Dinv[b];
+          tp.push_back(pack2(R0 + s, w));
+          tp.push_back(pack2(smalls[si].direct, 0));
+          for (int i = 0; i < w; i += 2)
+            tp.push_back(pack2(R0 + F.perm[s + i], i + 1 < w ? R0 + F.perm[s + i + 1] : 0));
           // packed by columns: forward lower (column j: rows j..w-1 of D),
           // backward upper (column j: rows 0..j of D^T, i.e. D[j][0..j])
           for (int j = 0; j < w; ++j) {
-            if (dir == 0) for (int i = j; i < w; ++i) T.dense.push_back(D[(size_t)i * w + j]);
-            else for (int i = 0; i <= j; ++i) T.dense.push_back(D[(size_t)j * w + i]);
+            if (dir == 0) for (int i = j; i < w; ++i) tp.push_back(dbits(D[(size_t)i * w + j]));
+            else for (int i = 0; i <= j; ++i) tp.push_back(dbits(D[(size_t)j * w + i]));
           }
-          T.sb_row0.push_back(s); T.sb_w.push_back(w); T.sb_off.push_back(off);
-          T.sb_direct.push_back(direct);
-        } else {
-          // packed by rows: forward row i = D[i][0..i]; backward row i of D^T =
-          // D[i..w-1][i]
-          for (int i = 0; i < w; ++i) {
-            if (dir == 0) for (int j = 0; j <= i; ++j) T.dense.push_back(D[(size_t)i * w + j]);
-            else for (int j = i; j < w; ++j) T.dense.push_back(D[(size_t)j * w + i]);
-          }
-          const int lb = (int)T.lb_row0.size();
-          T.lb_row0.push_back(s); T.lb_w.push_back(w); T.lb_off.push_back(off);
-          T.lb_direct.push_back(direct);
-          for (int i = 0; i < w; ++i) { T.lr_blk.push_back(lb); T.lr_i.push_back(i); }
+          out->stored_values += (int64_t)w * (w + 1) / 2;
+        }
+        for (int li : warp_large[wi]) {
+          const Large &lg = larges[li];
+          const int s = bp[lg.b], w = bp[lg.b + 1] - s, i = lg.i;
+          const std::vector<double> &D = Dinv[lg.b];
+          const int j0 = dir == 0 ? 0 : i;
+          tp.push_back(pack2(R0 + s + j0, lg.len));
+          tp.push_back(pack2(R0 + s + i, R0 + F.perm[s + i]));
+          // forward row i = D[i][0..i]; backward row i of D^T = D[i..w-1][i]
+          if (dir == 0) for (int j = 0; j <= i; ++j) tp.push_back(dbits(D[(size_t)i * w + j]));
+          else for (int j = i; j < w; ++j) tp.push_back(dbits(D[(size_t)j * w + i]));
+          out->stored_values += lg.len;
         }
       }
-      L.ta1 = (int)T.ta_row.size();
-      L.sb1 = (int)T.sb_row0.size();
-      L.lr1 = (int)T.lr_blk.size();
-      const double mean = npose_tasks ? (double)nblk_level / (double)npose_tasks : 0.0;
-      L.gpt = mean <= 3.0 ? 1 : mean <= 6.0 ? 2 : mean <= 12.0 ? 4 : 8;
-      L.pad = 0;
-      T.levels.push_back(L);
-    }
-    // scalar CSR of the off-diagonal entries whose source is not a pose column
-    // (or whose target row is a scalar row)
-    for (int r = 0; r < k; ++r) T.srowptr[r + 1] = T.srowptr[r] + scnt[r];
-    T.scol.resize(T.srowptr[k]);
-    T.sval.resize(T.srowptr[k]);
-    std::vector<int> fill(T.srowptr.begin(), T.srowptr.end() - 1);
-    for (int r = 0; r < k; ++r) {
-      const bool pose_row = F.pose_start[r] >= 0;
-      for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p) {
-        const int c = A.col[p];
-        if (pose_row && F.pose_start[c] >= 0) continue;
-        T.scol[fill[r]] = c;
-        T.sval[fill[r]++] = A.val[p];
+      // warps of a larger launch cluster than this agent's own (batches mix
+      // agent sizes; the work split of an agent depends on the agent alone, so
+      // its result does not depend on what it is batched with): barriers only
+      for (int wi = nwarps; wi < nwarps_total; ++wi) {
+        out->warp_tape[wi].push_back(pack2(0, a_present ? 1 : 0));
+        out->warp_tape[wi].push_back(pack2(0, 0));
       }
     }
-    for (int r = 0; r < k; ++r)
-      if (fill[r] != T.srowptr[r + 1]) return DCORA_ERR_ARG;
   }
+  for (std::vector<uint64_t> &tp : out->warp_tape)
+    while (tp.size() % TAPE_CHUNK_WORDS) tp.push_back(0);
   return DCORA_OK;
 }
 
-// CPU emulation of the device schedule (same grouping and operand pairing as
-// sptrsv.cu, sequential): x = (L L^T)^-1 b in FACTOR ordering.  Used only by
-// the host self check of the set-up code.
-void agent_trsv_apply_host(const AgentTrsv &S, int dh, const double *b, double *x) {
-  const int k = S.k;
-  std::vector<double> T(k), Y(k);
+// CPU replay of the tapes, warp by warp within a phase (phases are separated
+// by barriers on the device).
+void agent_tape_apply_host(const AgentTape &S, const double *b, double *x, double *T,
+                           double *Y) {
+  const int dh = S.dh, bs = dh * dh, nw = S.nwarps;
+  std::vector<size_t> pos(nw, 0);
+  struct Write { int row; double v; };
   for (int dir = 0; dir < 2; ++dir) {
-    const AgentTrsvDir &D = S.dir[dir];
-    for (const TrsvLevel &L : D.levels) {
-      for (int t = L.ta0; t < L.ta1; ++t) {
-        const int rr = D.ta_row[t];
-        const bool pose = rr >= 0;
-        const int r0 = pose ? rr : ~rr;
-        const int nr = pose ? dh : 1;
-        for (int a = 0; a < nr; ++a) {
+    for (int lv = 0; lv < S.nlev[dir]; ++lv) {
+      // phase A
+      for (int wi = 0; wi < nw; ++wi) {
+        const std::vector<uint64_t> &tp = S.warp_tape[wi];
+        size_t &p = pos[wi];
+        const int nrounds = lo32(tp[p]);
+        ++p;
+        for (int rd = 0; rd < nrounds; ++rd) {
+          const int niter = lo32(tp[p]), gpt = hi32(tp[p]);
+          ++p;
+          int r0[8], nrows[8], pb[8];
+          for (int g = 0; g < 8; ++g) {
+            r0[g] = lo32(tp[p]); nrows[g] = hi32(tp[p]); pb[g] = lo32(tp[p + 1]);
+            p += 2;
+          }
+          std::vector<double> acc(8 * 4, 0.0);
+          for (int it = 0; it < niter; ++it) {
+            int c[8];
+            for (int g = 0; g < 8; g += 2) { c[g] = lo32(tp[p]); c[g + 1] = hi32(tp[p]); ++p; }
+            for (int g = 0; g < 8; ++g)
+              for (int a = 0; a < dh; ++a)
+                for (int bb = 0; bb < dh; ++bb)
+                  acc[g * 4 + a] += bitsd(tp[p + (size_t)a * 8 * dh + g * dh + bb]) * Y[c[g] + bb];
+            p += 8 * bs;
+          }
+          for (int g = 0; g < 8; g += gpt) {
+            if (r0[g] < 0) continue;
+            for (int a = 0; a < nrows[g]; ++a) {
+              double s = 0.0;
+              for (int gg = 0; gg < gpt; ++gg) s += acc[(g + gg) * 4 + a];
+              const double rhs = dir == 0 ? b[pb[g] + a] : Y[r0[g] + a];
+              T[r0[g] + a] = rhs - s;
+            }
+          }
+        }
+      }
+      // phase B (writes applied after every warp has read: the device barrier)
+      std::vector<Write> writes;
+      for (int wi = 0; wi < nw; ++wi) {
+        const std::vector<uint64_t> &tp = S.warp_tape[wi];
+        size_t &p = pos[wi];
+        const int nsmall = lo32(tp[p]), nlarge = hi32(tp[p]);
+        ++p;
+        for (int s = 0; s < nsmall; ++s) {
+          const int r0 = lo32(tp[p]), w = hi32(tp[p]);
+          const int direct = lo32(tp[p + 1]);
+          p += 2;
+          std::vector<int> pm(w);
+          for (int i = 0; i < w; i += 2) {
+            pm[i] = lo32(tp[p]);
+            if (i + 1 < w) pm[i + 1] = hi32(tp[p]);
+            ++p;
+          }
+          std::vector<double> tv(w), acc(w, 0.0);
+          for (int i = 0; i < w; ++i) tv[i] = direct ? b[pm[i]] : T[r0 + i];
+          for (int j = 0; j < w; ++j) {
+            if (dir == 0) for (int i = j; i < w; ++i) acc[i] += bitsd(tp[p++]) * tv[j];
+            else for (int i = 0; i <= j; ++i) acc[i] += bitsd(tp[p++]) * tv[j];
+          }
+          for (int i = 0; i < w; ++i) {
+            writes.push_back({r0 + i, acc[i]});
+            if (dir == 1) x[pm[i]] = acc[i];
+          }
+        }
+        for (int l = 0; l < nlarge; ++l) {
+          const int src0 = lo32(tp[p]), len = hi32(tp[p]);
+          const int dest = lo32(tp[p + 1]), dperm = hi32(tp[p + 1]);
+          p += 2;
           double acc = 0.0;
-          if (pose)
-            for (int p = D.ta_bptr[t]; p < D.ta_bptr[t + 1]; ++p)
-              for (int c = 0; c < dh; ++c)
-                acc += D.bval[(size_t)p * dh * dh + a * dh + c] * Y[D.bcol[p] + c];
-          for (int p = D.srowptr[r0 + a]; p < D.srowptr[r0 + a + 1]; ++p)
-            acc += D.sval[p] * Y[D.scol[p]];
-          T[r0 + a] = (dir == 0 ? b[r0 + a] : Y[r0 + a]) - acc;
+          for (int j = 0; j < len; ++j) acc += bitsd(tp[p++]) * T[src0 + j];
+          writes.push_back({dest, acc});
+          if (dir == 1) x[dperm] = acc;
         }
       }
-      std::vector<double> tmp;
-      for (int s = L.sb0; s < L.sb1; ++s) {
-        const int r0 = D.sb_row0[s], w = D.sb_w[s];
-        const double *M = D.dense.data() + D.sb_off[s];
-        const double *src = D.sb_direct[s] ? b : T.data();
-        tmp.assign(w, 0.0);
-        size_t o = 0;
-        for (int j = 0; j < w; ++j) {
-          if (dir == 0) for (int i = j; i < w; ++i) tmp[i] += M[o++] * src[r0 + j];
-          else for (int i = 0; i <= j; ++i) tmp[i] += M[o++] * src[r0 + j];
-        }
-        for (int i = 0; i < w; ++i) Y[r0 + i] = tmp[i];
-      }
-      // large blocks: all rows read T, then write Y
-      std::vector<double> outv(L.lr1 - L.lr0);
-      for (int q = L.lr0; q < L.lr1; ++q) {
-        const int lb = D.lr_blk[q], i = D.lr_i[q];
-        const int r0 = D.lb_row0[lb], w = D.lb_w[lb];
-        const double *src = D.lb_direct[lb] ? b : T.data();
-        double acc = 0.0;
-        if (dir == 0) {
-          const double *row = D.dense.data() + D.lb_off[lb] + (int64_t)i * (i + 1) / 2;
-          for (int j = 0; j <= i; ++j) acc += row[j] * src[r0 + j];
-        } else {
-          const double *row = D.dense.data() + D.lb_off[lb] + (int64_t)i * w - (int64_t)i * (i - 1) / 2;
-          for (int j = i; j < w; ++j) acc += row[j - i] * src[r0 + j];
-        }
-        outv[q - L.lr0] = acc;
-      }
-      for (int q = L.lr0; q < L.lr1; ++q) Y[D.lb_row0[D.lr_blk[q]] + D.lr_i[q]] = outv[q - L.lr0];
+      for (const Write &wv : writes) Y[wv.row] = wv.v;
     }
   }
-  for (int i = 0; i < k; ++i) x[i] = Y[i];
 }
 
 }  // namespace dcora
