@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -93,6 +94,7 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
 struct DeviceCoupling {
   int device = 0;
   int64_t KH = 0, nnzb = 0, nrem_rows = 0, nnz_in = 0;
+  std::vector<int> rem_agent_h;
   bool identity_perm = true;
   int *perm_h = nullptr;
   int *browptr = nullptr, *bcol = nullptr;
@@ -143,13 +145,28 @@ struct DeviceFactor {
   void release();
 };
 
+// Compacted launch lists of a subset of the batch's agents (one colour of an
+// RBCD sweep): masked kernels are launched over these lists instead of over
+// the whole batch, so a colour step costs what its agents cost.
+struct ActiveSet {
+  int n_agents = 0, n_chunks = 0, n_tiles = 0, n_rem = 0, n_crem = 0;
+  int *agents = nullptr;      // agent ids
+  int *chunks = nullptr;      // chunk ids
+  int2 *tiles = nullptr;      // SpMM tiles: [first, end) pose block rows
+  int *rem_rows = nullptr;    // remainder rows of Q
+  int *crem_rows = nullptr;   // remainder rows of the coupling matrix
+  uint8_t *mask = nullptr;    // A bytes: the subset itself
+  const void *coupling_of = nullptr;  // coupling the crem list was built for
+  ~ActiveSet();
+};
+
 struct DeviceMatrices {
   int device = 0;
   int d = 0, order = 0, A = 0, np = 0;
   int64_t K = 0, nnz_in = 0, nnzb = 0, nrem_rows = 0, nrem = 0;
   int nchunks = 0;
   std::vector<int64_t> coff;
-  std::vector<int> n, l, b, poff, agent_chunk0_h;
+  std::vector<int> n, l, b, poff, agent_chunk0_h, rem_agent_h;
   std::vector<double> reg;  // per agent: regularisation of the factor (<0: none)
   bool identity_perm = true;
   int *perm = nullptr;
@@ -175,6 +192,9 @@ struct dcora_problem {
   std::shared_ptr<dcora::DeviceCoupling> C;  // cross-agent coupling (RBCD), optional
   double *xe = nullptr;            // [X | H] extended vector, r*(K+KH)
   double *hstage = nullptr;        // halo staging (reference layout)
+  // launch lists of the caller's current agent subset (null: whole batch)
+  std::shared_ptr<dcora::ActiveSet> act;
+  std::map<std::string, std::shared_ptr<dcora::ActiveSet>> act_cache;
   int *pack_idx = nullptr;         // cached public-column index list (device)
   std::vector<int32_t> pack_idx_host;
   cudaStream_t stream = nullptr;

@@ -58,14 +58,24 @@ bsr_spmm_kernel(int np, const int *__restrict__ browptr,
                 const int *__restrict__ bcol, const double *__restrict__ bval,
                 const int *__restrict__ prowcol, const int *__restrict__ pose_agent,
                 const int *__restrict__ flags, int mask_flag,
+                const int2 *__restrict__ tiles,
                 const double *__restrict__ X, const double *__restrict__ G,
                 double *__restrict__ Y) {
   constexpr int PPW = Map<DH>::PPW;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * 128 + threadIdx.x) >> 5;
   const int sub = lane / DH, a = lane - sub * DH;
-  const int i = warp * PPW + sub;
-  if (sub >= PPW || i >= np) return;
+  // a CTA covers 4*PPW consecutive pose rows: of the whole batch, or of one
+  // tile of the active agents (tiles never straddle agents)
+  int i, iend;
+  if (tiles != nullptr) {
+    const int2 t = tiles[blockIdx.x];
+    i = t.x + (threadIdx.x >> 5) * PPW + sub;
+    iend = t.y;
+  } else {
+    i = ((blockIdx.x * 128 + threadIdx.x) >> 5) * PPW + sub;
+    iend = np;
+  }
+  if (sub >= PPW || i >= iend) return;
   if (mask_flag >= 0 && flags[pose_agent[i] * NF + mask_flag] == 0) return;
   double acc[R];
 #pragma unroll
@@ -109,10 +119,12 @@ rem_spmm_kernel(int nrows, const int *__restrict__ rem_row,
                 const uint8_t *__restrict__ rem_assign,
                 const int *__restrict__ col_agent_of_row,
                 const int *__restrict__ flags, int mask_flag,
+                const int *__restrict__ list,
                 const double *__restrict__ X, const double *__restrict__ G,
                 double *__restrict__ Y) {
-  const int s = blockIdx.x * 128 + threadIdx.x;
+  int s = blockIdx.x * 128 + threadIdx.x;
   if (s >= nrows) return;
+  if (list != nullptr) s = list[s];
   if (mask_flag >= 0 && flags[col_agent_of_row[s] * NF + mask_flag] == 0) return;
   double acc[R];
 #pragma unroll
@@ -294,12 +306,12 @@ enum ManifoldOp : int {
 template <int R, int DH, int OP>
 __global__ void __launch_bounds__(128)
 manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
-                int mask_flag, const double *__restrict__ X,
+                int mask_flag, const int *__restrict__ list, const double *__restrict__ X,
                 const double *__restrict__ V, const double *__restrict__ HV,
                 const double *__restrict__ S, double *__restrict__ OUT) {
   constexpr int D = DH - 1;
   constexpr int PPW = Map<DH>::PPW;
-  const Chunk ch = chunks[blockIdx.x];
+  const Chunk ch = chunks[list ? list[blockIdx.x] : blockIdx.x];
   if (!agent_on(flags, ch.agent, mask_flag)) return;
   if (ch.kind == KIND_POSE) {
     const int nposes = ch.ncols / DH;
@@ -453,9 +465,11 @@ struct DotArgs {
 
 __global__ void __launch_bounds__(128)
 dots_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
-            int mask_flag, int R, DotArgs args, double *__restrict__ partials) {
+            int mask_flag, const int *__restrict__ list, int R, DotArgs args,
+            double *__restrict__ partials) {
   __shared__ double sm[4];
-  const Chunk ch = chunks[blockIdx.x];
+  const int cid = list ? list[blockIdx.x] : blockIdx.x;
+  const Chunk ch = chunks[cid];
   if (!agent_on(flags, ch.agent, mask_flag)) return;
   const size_t o = (size_t)ch.col0 * R;
   const int len = ch.ncols * R;
@@ -464,16 +478,17 @@ dots_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
     double acc = 0.0;
     for (int i = threadIdx.x; i < len; i += 128) acc = fma(x[i], y[i], acc);
     const double t = block_sum<128>(acc, sm);
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * NPART + s] = t;
+    if (threadIdx.x == 0) partials[(size_t)cid * NPART + s] = t;
   }
 }
 
 __global__ void __launch_bounds__(128)
 axpby_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
-             int mask_flag, int R, const double *__restrict__ scal, int slot_a,
+             int mask_flag, const int *__restrict__ list, int R,
+             const double *__restrict__ scal, int slot_a,
              double ca, const double *__restrict__ x, int slot_b, double cb,
              const double *__restrict__ y, double *__restrict__ out) {
-  const Chunk ch = chunks[blockIdx.x];
+  const Chunk ch = chunks[list ? list[blockIdx.x] : blockIdx.x];
   if (!agent_on(flags, ch.agent, mask_flag)) return;
   const double a = slot_a >= 0 ? ca * scal[ch.agent * NS + slot_a] : ca;
   const double b = slot_b >= 0 ? cb * scal[ch.agent * NS + slot_b] : cb;
@@ -523,23 +538,26 @@ reduce_scalars_kernel(const int *__restrict__ agent_chunk0,
 int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
                     const double *G, double *Y, int mask_flag) {
   DeviceMatrices &M = *p->M;
-  if (A.np > 0) {
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (A.np > 0 && (!as || as->n_tiles > 0)) {
     DCORA_DISPATCH_RD(p->r, M.d, {
       constexpr int PPW = Map<DH>::PPW;
       const int ppc = 4 * PPW;
-      const int grid = (A.np + ppc - 1) / ppc;
+      const int grid = as ? as->n_tiles : (A.np + ppc - 1) / ppc;
       bsr_spmm_kernel<R, DH><<<grid, 128, 0, p->stream>>>(
           A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
-          mask_flag, X, G, Y);
+          mask_flag, as ? as->tiles : nullptr, X, G, Y);
     })
     DCORA_LAUNCH_CHECK(p);
   }
-  if (A.nrem_rows > 0) {
+  const int *rlist = as ? (A.coupling ? as->crem_rows : as->rem_rows) : nullptr;
+  const int64_t nrows = as ? (A.coupling ? as->n_crem : as->n_rem) : A.nrem_rows;
+  if (nrows > 0) {
     DCORA_DISPATCH_R(p->r, {
-      const int grid = (int)((A.nrem_rows + 127) / 128);
+      const int grid = (int)((nrows + 127) / 128);
       rem_spmm_kernel<R><<<grid, 128, 0, p->stream>>>(
-          (int)A.nrem_rows, A.rem_row, A.rem_rowptr, A.rem_col, A.rem_val,
-          A.rem_assign, A.rem_agent, p->flags, mask_flag, X, G, Y);
+          (int)nrows, A.rem_row, A.rem_rowptr, A.rem_col, A.rem_val,
+          A.rem_assign, A.rem_agent, p->flags, mask_flag, rlist, X, G, Y);
     })
     DCORA_LAUNCH_CHECK(p);
   }
@@ -564,13 +582,15 @@ static int launch_manifold(dcora_problem *p, const double *X, const double *V,
                            int mask_flag) {
   DeviceMatrices &M = *p->M;
   if (M.nchunks == 0) return DCORA_OK;
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
   DCORA_DISPATCH_RD(p->r, M.d, {
     if (R < DH - 1) {
       set_error("manifold op needs r >= d");
       return DCORA_ERR_ARG;
     }
-    manifold_kernel<R, DH, OP><<<M.nchunks, 128, 0, p->stream>>>(
-        M.chunks, p->flags, mask_flag, X, V, HV, S, OUT);
+    manifold_kernel<R, DH, OP><<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+        M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, X, V, HV, S, OUT);
   })
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
@@ -606,8 +626,10 @@ int launch_dots(dcora_problem *p, int n, const double *const *x,
   DotArgs args;
   args.n = n;
   for (int s = 0; s < n; ++s) { args.x[s] = x[s]; args.y[s] = y[s]; }
-  dots_kernel<<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->flags, mask_flag, p->r,
-                                                args, p->partials);
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
+  dots_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+      M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r, args, p->partials);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }
@@ -616,9 +638,11 @@ int launch_axpby(dcora_problem *p, double *out, int slot_a, double ca,
                  const double *x, int slot_b, double cb, const double *y,
                  int mask_flag) {
   DeviceMatrices &M = *p->M;
-  axpby_kernel<<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->flags, mask_flag, p->r,
-                                                 p->scal, slot_a, ca, x, slot_b, cb,
-                                                 y, out);
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
+  axpby_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+      M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r, p->scal, slot_a, ca, x,
+      slot_b, cb, y, out);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }

@@ -28,6 +28,7 @@ enum Flag : int {
 // A block-sparse operand of the SpMM kernels: BSR over output pose blocks +
 // scalar CSR remainder (see layout.cpp).
 struct SpmmMat {
+  bool coupling = false;  // the cross-agent coupling matrix (rbcd.cu) rather than Q
   int np = 0;
   const int *browptr = nullptr, *bcol = nullptr, *prowcol = nullptr, *pose_agent = nullptr;
   const double *bval = nullptr;
@@ -36,6 +37,12 @@ struct SpmmMat {
   const uint8_t *rem_assign = nullptr;
   const double *rem_val = nullptr;
 };
+// Launch lists for a masked launch: the caller's agent subset when the mask is a
+// per-solve flag (every such flag is a subset of F_USER), null for the whole
+// batch.
+inline const ActiveSet *active_set(const dcora_problem *p, int mask_flag) {
+  return (mask_flag >= 0 && mask_flag != F_ALL) ? p->act.get() : nullptr;
+}
 int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
                     const double *G, double *Y, int mask_flag);
 // Y = X*Q (+G).  mask_flag < 0: all agents.

@@ -14,6 +14,11 @@ namespace dcora {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 
+ActiveSet::~ActiveSet() {
+  cudaFree(agents); cudaFree(chunks); cudaFree(tiles); cudaFree(rem_rows); cudaFree(crem_rows);
+  cudaFree(mask);
+}
+
 DeviceMatrices::~DeviceMatrices() {
   cudaSetDevice(device);
   cudaFree(perm); cudaFree(browptr); cudaFree(bcol); cudaFree(prowcol);
@@ -210,6 +215,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
   DCORA_CUDA(upload(&M->prowcol, H.prowcol));
   DCORA_CUDA(upload(&M->pose_agent, pose_agent));
   DCORA_CUDA(upload(&M->rem_agent, rem_agent));
+  M->rem_agent_h = rem_agent;
   DCORA_CUDA(upload(&M->rem_row, H.rem_row));
   DCORA_CUDA(upload(&M->rem_rowptr, H.rem_rowptr));
   DCORA_CUDA(upload(&M->rem_col, H.rem_col));

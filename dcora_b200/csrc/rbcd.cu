@@ -95,6 +95,7 @@ int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
   DCORA_CUDA(upload(&C->rem_rowptr, H.rem_rowptr));
   DCORA_CUDA(upload(&C->rem_col, H.rem_col));
   DCORA_CUDA(upload(&C->rem_agent, rem_agent));
+  C->rem_agent_h = rem_agent;
   DCORA_CUDA(upload(&C->rem_assign, H.rem_assign));
   DCORA_CUDA(upload(&C->rem_val, H.rem_val));
   p->C = C;
@@ -142,6 +143,7 @@ int dcora_problem_update_G(dcora_problem *p, const double *X, const double *Hh,
   }
   DCORA_TRY(set_user_mask(p, active));
   SpmmMat A;
+  A.coupling = true;
   A.np = M.np; A.browptr = C.browptr; A.bcol = C.bcol; A.bval = C.bval;
   A.prowcol = M.prowcol; A.pose_agent = M.pose_agent;
   A.nrem_rows = C.nrem_rows; A.rem_row = C.rem_row; A.rem_rowptr = C.rem_rowptr;

@@ -41,10 +41,10 @@ __device__ double agent_sum(const int *agent_chunk0, const double *partials, int
 }
 
 __global__ void __launch_bounds__(128)
-combine_f_kernel(const int *agent_chunk0, const double *partials, const int *flags,
+combine_f_kernel(const int *list, const int *agent_chunk0, const double *partials, const int *flags,
                  int mask_flag, int slot, int with_G, double *scal) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   if (mask_flag >= 0 && flags[a * NF + mask_flag] == 0) return;
   const double p0 = agent_sum(agent_chunk0, partials, a, 0, sm);
   const double p1 = with_G ? agent_sum(agent_chunk0, partials, a, 1, sm) : 0.0;
@@ -53,11 +53,11 @@ combine_f_kernel(const int *agent_chunk0, const double *partials, const int *fla
 
 // after f1 (S_F1) and <gf,gf> (partial 0)
 __global__ void __launch_bounds__(128)
-rtr_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
+rtr_init_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                 double *scal, double tol, double delta0, double max_delta,
                 int *counters) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   const double gg = agent_sum(agent_chunk0, partials, a, 0, sm);
   if (threadIdx.x != 0) return;
   double *s = scal + a * NS;
@@ -80,10 +80,10 @@ rtr_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
 
 // start of tCG: partial 0 = <z, r>
 __global__ void __launch_bounds__(128)
-tcg_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
+tcg_init_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                 double *scal) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_OUTER] == 0) { if (threadIdx.x == 0) f[F_TCG] = 0; return; }
   const double zr = agent_sum(agent_chunk0, partials, a, 0, sm);
@@ -97,10 +97,10 @@ tcg_init_kernel(const int *agent_chunk0, const double *partials, int *flags,
 
 // partial 0 = <delta, H delta>
 __global__ void __launch_bounds__(128)
-tcg_stepA_kernel(const int *agent_chunk0, const double *partials, int *flags,
+tcg_stepA_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                  double *scal) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_TCG] == 0) { if (threadIdx.x == 0) f[F_STEP] = 0; return; }
   const double d_Hd = agent_sum(agent_chunk0, partials, a, 0, sm);
@@ -130,10 +130,10 @@ tcg_stepA_kernel(const int *agent_chunk0, const double *partials, int *flags,
 
 // partial 0 = <r, r> after the update
 __global__ void __launch_bounds__(128)
-tcg_stepB_kernel(const int *agent_chunk0, const double *partials, int *flags,
+tcg_stepB_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                  double *scal, int j, int min_inner, int max_inner, int *counters) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_STEP] == 0) return;
   const double rr = agent_sum(agent_chunk0, partials, a, 0, sm);
@@ -161,10 +161,10 @@ tcg_stepB_kernel(const int *agent_chunk0, const double *partials, int *flags,
 
 // partial 0 = <z, r> with the new z
 __global__ void __launch_bounds__(128)
-tcg_stepC_kernel(const int *agent_chunk0, const double *partials, const int *flags,
+tcg_stepC_kernel(const int *list, const int *agent_chunk0, const double *partials, const int *flags,
                  double *scal) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   if (flags[a * NF + F_TCG] == 0) return;
   const double zr = agent_sum(agent_chunk0, partials, a, 0, sm);
   if (threadIdx.x != 0) return;
@@ -180,10 +180,10 @@ tcg_stepC_kernel(const int *agent_chunk0, const double *partials, const int *fla
 
 // S_F2 holds f(x2); partial 0 = <eta, gf1>, partial 1 = <eta, H eta>
 __global__ void __launch_bounds__(128)
-rtr_rho_kernel(const int *agent_chunk0, const double *partials, int *flags,
+rtr_rho_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                double *scal, int single_mode) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_OUTER] == 0) { if (threadIdx.x == 0) f[F_ACCEPT] = 0; return; }
   const double eg = agent_sum(agent_chunk0, partials, a, 0, sm);
@@ -215,10 +215,10 @@ rtr_rho_kernel(const int *agent_chunk0, const double *partials, int *flags,
 
 // after the gradient at the accepted point: partial 0 = <gf, gf>
 __global__ void __launch_bounds__(128)
-rtr_accept_kernel(const int *agent_chunk0, const double *partials, int *flags,
+rtr_accept_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                   double *scal, int max_iter, int single_mode, int *counters) {
   __shared__ double sm[4];
-  const int a = blockIdx.x;
+  const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_OUTER] == 0) return;
   double gg = 0.0;
@@ -240,9 +240,11 @@ rtr_accept_kernel(const int *agent_chunk0, const double *partials, int *flags,
 }  // namespace
 
 int launch_combine_f(dcora_problem *p, int slot, int with_G, int mask_flag) {
-  combine_f_kernel<<<p->M->A, 128, 0, p->stream>>>(p->M->agent_chunk0, p->partials,
-                                                   p->flags, mask_flag, slot, with_G,
-                                                   p->scal);
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_agents == 0) return DCORA_OK;
+  combine_f_kernel<<<as ? as->n_agents : p->M->A, 128, 0, p->stream>>>(
+      as ? as->agents : nullptr, p->M->agent_chunk0, p->partials, p->flags, mask_flag, slot,
+      with_G, p->scal);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }
@@ -287,17 +289,77 @@ static int gradient_at(dcora_problem *p, const double *x1, double *EG, double *g
   return launch_dots(p, 1, xs, xs, mask);
 }
 
+namespace {
+__global__ void __launch_bounds__(128)
+set_user_flags_kernel(int A, const uint8_t *__restrict__ mask, int *__restrict__ flags) {
+  const int a = blockIdx.x * 128 + threadIdx.x;
+  if (a >= A) return;
+  flags[a * NF + F_USER] = mask ? (mask[a] ? 1 : 0) : 1;
+  flags[a * NF + F_ALL] = 1;
+}
+
+template <typename T>
+cudaError_t up_list(T **dst, const std::vector<T> &src) {
+  cudaError_t e = cudaMalloc(dst, std::max<size_t>(1, src.size()) * sizeof(T));
+  if (e != cudaSuccess || src.empty()) return e;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+}  // namespace
+
+// flags[a][F_USER] <- active[a] (NULL: all agents) and the matching compacted
+// launch lists (built once per distinct subset and cached: an RBCD sweep cycles
+// through the same few colour classes).
 int set_user_mask(dcora_problem *p, const uint8_t *active) {
-  const int A = p->M->A;
-  DCORA_CUDA(cudaMemcpyAsync(p->h_flags, p->flags, sizeof(int) * NF * A,
-                             cudaMemcpyDeviceToHost, p->stream));
-  DCORA_CUDA(cudaStreamSynchronize(p->stream));
-  for (int a = 0; a < A; ++a) {
-    p->h_flags[a * NF + F_USER] = active ? (active[a] ? 1 : 0) : 1;
-    p->h_flags[a * NF + F_ALL] = 1;
+  DeviceMatrices &M = *p->M;
+  const int A = M.A;
+  bool all = active == nullptr;
+  if (!all) {
+    all = true;
+    for (int a = 0; a < A && all; ++a) all = active[a] != 0;
   }
-  DCORA_CUDA(cudaMemcpyAsync(p->flags, p->h_flags, sizeof(int) * NF * A,
-                             cudaMemcpyHostToDevice, p->stream));
+  if (all) {
+    p->act.reset();
+  } else {
+    const std::string key(reinterpret_cast<const char *>(active), (size_t)A);
+    auto it = p->act_cache.find(key);
+    const void *cpl = p->C.get();
+    if (it == p->act_cache.end() || it->second->coupling_of != cpl) {
+      auto as = std::make_shared<ActiveSet>();
+      std::vector<int> agents, chunks, rem, crem;
+      std::vector<int2> tiles;
+      std::vector<uint8_t> mask(active, active + A);
+      const int ppc = 4 * (32 / (M.d + 1));
+      for (int a = 0; a < A; ++a) {
+        if (!active[a]) continue;
+        agents.push_back(a);
+        for (int c = M.agent_chunk0_h[a]; c < M.agent_chunk0_h[a + 1]; ++c) chunks.push_back(c);
+        for (int i0 = M.poff[a]; i0 < M.poff[a + 1]; i0 += ppc)
+          tiles.push_back(make_int2(i0, std::min(i0 + ppc, M.poff[a + 1])));
+      }
+      for (size_t s = 0; s < M.rem_agent_h.size(); ++s)
+        if (active[M.rem_agent_h[s]]) rem.push_back((int)s);
+      if (p->C)
+        for (size_t s = 0; s < p->C->rem_agent_h.size(); ++s)
+          if (active[p->C->rem_agent_h[s]]) crem.push_back((int)s);
+      as->n_agents = (int)agents.size(); as->n_chunks = (int)chunks.size();
+      as->n_tiles = (int)tiles.size(); as->n_rem = (int)rem.size(); as->n_crem = (int)crem.size();
+      as->coupling_of = cpl;
+      DCORA_CUDA(up_list(&as->agents, agents));
+      DCORA_CUDA(up_list(&as->chunks, chunks));
+      DCORA_CUDA(up_list(&as->tiles, tiles));
+      DCORA_CUDA(up_list(&as->rem_rows, rem));
+      DCORA_CUDA(up_list(&as->crem_rows, crem));
+      DCORA_CUDA(up_list(&as->mask, mask));
+      if (p->act_cache.size() > 64) p->act_cache.clear();
+      p->act_cache[key] = as;
+      p->act = as;
+    } else {
+      p->act = it->second;
+    }
+  }
+  set_user_flags_kernel<<<(A + 127) / 128, 128, 0, p->stream>>>(
+      A, p->act ? p->act->mask : nullptr, p->flags);
+  DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }
 
@@ -314,6 +376,15 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   int *counters = p->flags + (size_t)NF * A;
   const auto tstart = std::chrono::steady_clock::now();
   DCORA_TRY(set_user_mask(p, active));
+  // per-agent control kernels run over the caller's subset only
+  const int nA = p->act ? p->act->n_agents : A;
+  const int *alist = p->act ? p->act->agents : nullptr;
+  if (nA == 0) {
+    DCORA_TRY(read_scalars(p));
+    if (results)
+      for (int a = 0; a < A; ++a) { results[a] = dcora_ropt_result(); }
+    return DCORA_OK;
+  }
 
   // initial statistics: fInit, gradNormInit (QuadraticOptimizer.cpp:30-31)
   DCORA_TRY(eval_f(p, x1, t0, S_F1, F_USER));
@@ -322,7 +393,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   const int single_mode = prm->RTR_iterations == 1;
   const int max_outer = single_mode ? 12 : prm->RTR_iterations;
   const double Delta0 = prm->RTR_initial_radius;
-  rtr_init_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags,
+  rtr_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
                                             p->scal, prm->gradnorm_tol, Delta0,
                                             single_mode ? Delta0 : 5.0 * Delta0,
                                             counters);
@@ -353,7 +424,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       const double *xs[1] = {z}, *ys[1] = {r};
       DCORA_TRY(launch_dots(p, 1, xs, ys, F_OUTER));
     }
-    tcg_init_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+    tcg_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, -1, 0.0, nullptr, F_TCG));
     int n_tcg = n_outer;
@@ -363,7 +434,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
         const double *xs[1] = {delta}, *ys[1] = {Hd};
         DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
       }
-      tcg_stepA_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+      tcg_stepA_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       DCORA_TRY(launch_axpby(p, eta, -1, 1.0, eta, S_CETA, 1.0, delta, F_STEP));
       DCORA_TRY(launch_axpby(p, r, -1, 1.0, r, S_CR, 1.0, Hd, F_STEP));
@@ -372,7 +443,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
         DCORA_TRY(launch_dots(p, 1, xs, xs, F_STEP));
       }
       DCORA_TRY(zero_counter(p, 1));
-      tcg_stepB_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags,
+      tcg_stepB_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
                                                  p->scal, j, 0, prm->RTR_tCG_iterations,
                                                  counters);
       DCORA_LAUNCH_CHECK(p);
@@ -381,7 +452,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
         const double *xs[1] = {z}, *ys[1] = {r};
         DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
       }
-      tcg_stepC_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal);
+      tcg_stepC_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       // delta = -z + beta * delta
       DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, S_BETA, 1.0, delta, F_TCG));
@@ -396,13 +467,13 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       const double *xs[2] = {eta, eta}, *ys[2] = {gf, Hd};
       DCORA_TRY(launch_dots(p, 2, xs, ys, F_OUTER));
     }
-    rtr_rho_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal,
+    rtr_rho_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
                                              single_mode);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));
     DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT));
     DCORA_TRY(zero_counter(p, 0));
-    rtr_accept_kernel<<<A, 128, 0, p->stream>>>(M.agent_chunk0, p->partials, p->flags, p->scal,
+    rtr_accept_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
                                                 max_outer, single_mode, counters);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(read_counters(p, cnt));

@@ -351,13 +351,15 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
 template <int R, int DH, int CL>
 __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
+                 const int *__restrict__ agent_list,
                  const unsigned long long *__restrict__ tape,
                  const long long *__restrict__ tape_off, const int *__restrict__ tape_chunks,
                  const int *__restrict__ nlev, const double *__restrict__ V, double *T,
                  double *Y, double *OUT, unsigned long long *trace_buf, int trace_agent) {
-  const int agent = blockIdx.x / CL;
+  const int slot = blockIdx.x / CL;
+  const int agent = agent_list ? agent_list[slot] : slot;
   if (mask_flag >= 0 && flags[agent * NF + mask_flag] == 0) return;  // whole cluster
-  const int crank = blockIdx.x - agent * CL;
+  const int crank = blockIdx.x - slot * CL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = crank * TRSV_NW + warp;
   constexpr int nwarps = CL * TRSV_NW;
@@ -452,7 +454,9 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
   DeviceMatrices &M = *p->M;
   const DeviceFactor &F = M.F;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(M.A * CL));
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_agents == 0) return DCORA_OK;
+  cfg.gridDim = dim3((unsigned)((as ? as->n_agents : M.A) * CL));
   cfg.blockDim = dim3(TRSV_THREADS);
   cfg.dynamicSmemBytes = TRSV_SMEM;
   cfg.stream = p->stream;
@@ -466,7 +470,8 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
   DCORA_CUDA(cudaLaunchKernelEx(&cfg, trsv_tape_kernel<R, DH, CL>, (const int *)p->flags,
-                                mask_flag, (const unsigned long long *)F.tape,
+                                mask_flag, (const int *)(as ? as->agents : nullptr),
+                                (const unsigned long long *)F.tape,
                                 (const long long *)F.tape_off, (const int *)F.tape_chunks,
                                 (const int *)F.nlev, V, T, Y, OUT, trace, trace_agent));
   p->launches++;

@@ -34,16 +34,20 @@ def test_ground_truth_is_a_fixed_point(name):
     assert res.lambda_min > -1e-6
 
 
-@pytest.mark.parametrize("name,r,tol", [("smallGrid3D", 5, 1e-6),
-                                        ("tinyGrid3D", 4, 1e-7),
-                                        ("range_aided_slam_test_3d", 5, 1e-7)])
-def test_rtr_converged_cost_matches_oracle(name, r, tol):
-    # north_star: final cost relative error <= 1e-8 at the same tolerance
+@pytest.mark.parametrize("name,r,tol,iters", [("smallGrid3D", 5, 1e-6, 300),
+                                              ("tinyGrid3D", 4, 1e-7, 300),
+                                              ("range_aided_slam_test_3d", 5, 1e-7, 3000)])
+def test_rtr_converged_cost_matches_oracle(name, r, tol, iters):
+    # north_star: final cost relative error <= 1e-8 at the same tolerance.
+    # The range-aided fixture is noiseless (f* = 0, so the bound is taken
+    # relative to fInit) and, with the reference's tiny RA regularisation
+    # lambda_max/(1e6-1) (Graph.cpp:1919-1960), RTR needs ~600 outer iterations
+    # from a random point on the CPU oracle as well.
     import dcora_b200 as dc
     P, g, info = central_problem(name, r)
     gp = gpu_problem(P)
     X0 = mf.random_point(P.L, np.random.default_rng(1))
-    kw = dict(RTR_iterations=300, RTR_tCG_iterations=500, gradnorm_tol=tol)
+    kw = dict(RTR_iterations=iters, RTR_tCG_iterations=500, gradnorm_tol=tol)
     oo = solver.QuadraticOptimizer(P, solver.ROptParameters(**kw))
     Xo = oo.optimize(X0)
     go = dc.QuadraticOptimizer(gp, _params(**kw))
@@ -51,9 +55,10 @@ def test_rtr_converged_cost_matches_oracle(name, r, tol):
     rg = go.getOptResult()
     assert rg.gradNormOpt < tol
     assert abs(rg.fInit - oo.result.fInit) <= 1e-12 * abs(oo.result.fInit)
-    assert abs(rg.fOpt - oo.result.fOpt) <= 1e-8 * abs(oo.result.fOpt)
+    assert oo.result.gradNormOpt < tol
+    assert abs(rg.fOpt - oo.result.fOpt) <= 1e-8 * abs(oo.result.fOpt) + 1e-13 * abs(rg.fInit)
     # the returned statistics are those of the returned point
-    assert abs(P.f(Xg) - rg.fOpt) <= 1e-10 * abs(rg.fOpt)
+    assert abs(P.f(Xg) - rg.fOpt) <= 1e-10 * abs(rg.fOpt) + 1e-13 * abs(rg.fInit)
     assert abs(P.rgrad_norm(Xg) - rg.gradNormOpt) <= 1e-6 * tol + 1e-12
 
 
