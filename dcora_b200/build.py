@@ -58,5 +58,34 @@ def build(verbose=False):
     return LIB
 
 
+EXAMPLES = os.path.join(HERE, "..", "examples")
+EXAMPLE_BIN = os.path.join(EXAMPLES, "bin")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_examples(verbose=False):
+    """C++ host-side programs written against include/dcora_b200/DCORA.hpp
+    (plain g++; they only link the C-ABI library)."""
+    os.makedirs(EXAMPLE_BIN, exist_ok=True)
+    out = []
+    inc = os.path.join(HERE, "..", "include")
+    for name in sorted(os.listdir(EXAMPLES)):
+        if not name.endswith(".cpp"):
+            continue
+        src = os.path.join(EXAMPLES, name)
+        exe = os.path.join(EXAMPLE_BIN, name[:-4])
+        deps = [src, os.path.join(inc, "dcora_b200.h"), os.path.join(inc, "dcora_b200", "DCORA.hpp")]
+        if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            cmd = [CXX, "-std=c++17", "-O2", "-Wall", "-I", inc, src, "-L", HERE, "-ldcora_b200",
+                   "-Wl,-rpath,$ORIGIN/../../dcora_b200", "-Wl,-rpath,/usr/local/cuda/lib64",
+                   "-o", exe]
+            subprocess.run(cmd, check=True)
+        out.append(exe)
+        if verbose:
+            print("built", exe)
+    return out
+
+
 if __name__ == "__main__":
     build(verbose=True)
+    build_examples(verbose=True)

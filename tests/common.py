@@ -109,3 +109,35 @@ def product_measurements(meas, num_robots=None):
         rg_range=rg.range, rg_prec=rg.precision, rg_w=rg.weight)
     part = pg.Partition(A, np.repeat(np.arange(A), n_a), np.repeat(np.arange(A), b_a))
     return M, part
+
+
+def write_g2o(path, meas, name=None):
+    """Write the pose-pose measurements of a golden fixture as a g2o file whose
+    information matrices reproduce kappa / tau under the reference reader's
+    formulas (DCORA_utils.cpp:288-292,337-346): Itt = tau I, Irr = 2 kappa I (3-D),
+    I33 = kappa (2-D).  No VERTEX lines (like data/kitti_00.g2o).  3-D rotations
+    are written from the raw file quaternions (tests/golden/quats.npz) when the
+    dataset `name` has them: the reference reader does not normalise quaternions."""
+    from scipy.spatial.transform import Rotation
+    pp = meas.pp
+    d = meas.d
+    with open(path, "w") as fh:
+        if d == 3:
+            quats = np.load(os.path.join(GOLDEN, "quats.npz"))
+            q = quats[name] if name in quats.files else Rotation.from_matrix(pp.R).as_quat()
+            for e in range(len(pp)):
+                tau, kap = pp.tau[e], pp.kappa[e]
+                info = np.zeros((6, 6))
+                info[:3, :3] = tau * np.eye(3)
+                info[3:, 3:] = 2.0 * kap * np.eye(3)
+                up = [info[a, b] for a in range(6) for b in range(a, 6)]
+                vals = list(pp.t[e]) + list(q[e]) + up
+                fh.write(f"EDGE_SE3:QUAT {pp.p1[e]} {pp.p2[e]} " +
+                         " ".join(f"{v:.17g}" for v in vals) + "\n")
+        else:
+            th = np.arctan2(pp.R[:, 1, 0], pp.R[:, 0, 0])
+            for e in range(len(pp)):
+                tau, kap = pp.tau[e], pp.kappa[e]
+                vals = [pp.t[e][0], pp.t[e][1], th[e], tau, 0.0, 0.0, tau, 0.0, kap]
+                fh.write(f"EDGE_SE2 {pp.p1[e]} {pp.p2[e]} " +
+                         " ".join(f"{v:.17g}" for v in vals) + "\n")

@@ -1,0 +1,62 @@
+"""Oracle known-answers for the dataset configs (BASELINE.json configs[1..3]).
+
+Run in the build container (minutes of CPU):
+    python tests/golden/make_expected.py [name ...]
+For each dataset the CPU oracle (oracle/solver.py, restating QuadraticOptimizer +
+ROPTLIB RTR/tCG) is run from a seeded random point at rank R0 to gradnorm <= TOL,
+the dual certificate S = Q - Lambda is formed (oracle/certify.py, restating
+DCORA_utils.cpp:1898-1982) and lambda_min(S) computed with ARPACK.  Results go to
+tests/golden/expected.json; the GPU parity tests (tests/test_gpu_datasets.py) compare
+the CUDA path against these numbers on the GPU box, where the oracle solve would be
+too slow to repeat.  The seed, rank and tolerance are recorded per entry.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import certify, manifold as mf, solver  # noqa: E402
+from tests.common import central_problem  # noqa: E402
+
+CASES = {  # name: (rank, seed, gradnorm tol, eta)
+    "smallGrid3D": (5, 1, 1e-6, 1e-3),
+    "kitti_00": (5, 1, 1e-5, 1e-3),
+    "sphere2500": (5, 1, 1e-5, 1e-3),
+    "torus3D": (5, 1, 1e-5, 1e-3),
+    "city10000": (5, 1, 1e-4, 1e-3),
+    "tiers": (4, 1, 1e-4, 1e-4),
+}
+
+
+def main():
+    path = os.path.join(HERE, "expected.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    for name in (sys.argv[1:] or CASES):
+        r, seed, tol, eta = CASES[name]
+        t0 = time.time()
+        P, g, info = central_problem(name, r)
+        X0 = mf.random_point(P.L, np.random.default_rng(seed))
+        opt = solver.QuadraticOptimizer(P, solver.ROptParameters(
+            RTR_iterations=2000, RTR_tCG_iterations=500, gradnorm_tol=tol))
+        X = opt.optimize(X0)
+        res = opt.result
+        S = certify.certificate_matrix(P.L, X, P.Q)
+        lam = float(certify.lambda_min(S))
+        psd = bool(certify.fast_verification(S, eta)[0])
+        out[name] = dict(r=r, seed=seed, gradnorm_tol=tol, eta=eta, fInit=res.fInit, fOpt=res.fOpt,
+                         cost_2f=2 * res.fOpt, gradNormOpt=res.gradNormOpt,
+                         outer_iters=res.outer_iters, inner_iters=res.inner_iters,
+                         lambda_min=lam, is_psd=psd, oracle_seconds=time.time() - t0)
+        print(name, out[name], flush=True)
+        with open(path, "w") as fh:
+            json.dump(out, fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,29 @@ def pack_meas(m):
     return out
 
 
+def raw_quaternions():
+    """quats.npz: the EDGE_SE3:QUAT quaternions (qx qy qz qw) exactly as written in the
+    data files.  The reference reader does not normalise them
+    (Eigen::Quaterniond(..).toRotationMatrix(), DCORA_utils.cpp:331), so the measured
+    rotations are slightly non-orthogonal; tests/common.write_g2o needs the raw values
+    to regenerate a g2o file that parses to bit-identical measurements."""
+    out = {}
+    for name in G2O:
+        q = []
+        with open(DATA + name + ".g2o") as fh:
+            for line in fh:
+                tok = line.split()
+                if tok and tok[0] == "EDGE_SE3:QUAT":
+                    q.append([float(v) for v in tok[6:10]])
+        if q:
+            out[name] = np.array(q)
+    np.savez_compressed(os.path.join(HERE, "quats.npz"), **out)
+    print("quats:", {k: v.shape for k, v in out.items()})
+
+
 def main():
+    if "--quats" in sys.argv:
+        return raw_quaternions()
     for name in G2O:
         meas, n, gt = dataio.read_g2o(DATA + name + ".g2o")
         d = meas.d
@@ -58,6 +80,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="pyfg", n=n, l=l, b=b,
                             has_gt=True, X_gt=X, **pack_meas(meas), **extra)
         print(name, "d", ds.dim, "n", n, "l", l, "b", b)
+    raw_quaternions()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,68 @@
+"""C++ host mirror (include/dcora_b200/DCORA.hpp) and the staircase example built on it."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.common import GOLDEN, central_problem, load_golden, write_g2o
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from dcora_b200 import build
+    build.build()
+    return [e for e in build.build_examples() if e.endswith("staircase_pgo")][0]
+
+
+def _run(exe, *args):
+    out = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    return out, lines
+
+
+@pytest.mark.parametrize("name", ["tinyGrid3D", "smallGrid3D", "kitti_00", "sphere2500"])
+def test_cpp_reader_and_Q_builder_match_oracle(exe, tmp_path, name):
+    # read_g2o_file + Graph::constructQuadraticCostTermPGO restated in C++ vs the oracle's Q
+    meas, info = load_golden(name)
+    path = tmp_path / (name + ".g2o")
+    write_g2o(path, meas, name)
+    out, lines = _run(exe, path, "--check-q")
+    assert out.returncode == 0, out.stderr
+    got = lines[-1]
+    P, g, _ = central_problem(name, info["d"] + 1, use_precond=False)
+    Q = P.Q.tocoo()
+    assert got["n"] == info["n"] and got["k"] == Q.shape[0]
+    fro = float(np.sqrt(np.sum(Q.data ** 2)))
+    chk = float(np.sum(Q.data * np.cos(0.001 * Q.row + 0.002 * Q.col)))
+    assert abs(got["fro"] - fro) <= 1e-12 * fro
+    assert abs(got["checksum"] - chk) <= 1e-10 * fro
+    assert got["nnz"] >= P.Q.nnz      # explicit zeros may be kept
+
+
+def test_cpp_precondition_violations_abort(exe, tmp_path):
+    # glog CHECK semantics: malformed input aborts the process
+    path = tmp_path / "bad.g2o"
+    path.write_text("EDGE_SE9 0 1 2 3\n")
+    out, _ = _run(exe, path, "--check-q")
+    assert out.returncode != 0 and "Check failed" in out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["smallGrid3D", "sphere2500", "torus3D"])
+def test_cpp_staircase_reaches_the_certified_optimum(exe, tmp_path, name):
+    exp_path = os.path.join(GOLDEN, "expected.json")
+    expected = json.load(open(exp_path))
+    if name not in expected:
+        pytest.skip("no oracle known-answer recorded for " + name)
+    e = expected[name]
+    meas, info = load_golden(name)
+    path = tmp_path / (name + ".g2o")
+    write_g2o(path, meas, name)
+    out, lines = _run(exe, path, "--rmin", e["r"], "--tol", e["gradnorm_tol"], "--eta", e["eta"])
+    assert out.returncode == 0, out.stdout + out.stderr
+    s = lines[-1]
+    assert s["summary"] and s["certified"] == e["is_psd"]
+    assert abs(s["cost_2f"] - e["cost_2f"]) <= 1e-8 * abs(e["cost_2f"])
+    assert s["lambda_min"] > -e["eta"]
