@@ -376,7 +376,8 @@ class QuadraticOptimizer:
     def __init__(self, problem: QuadraticProblem, params: ROptParameters | None = None):
         self.problem = problem
         self.params = params or ROptParameters()
-        self.results: list[ROPTResult] = []
+        self._raw = ()
+        self._results: list[ROPTResult] | None = []
 
     # setters (QuadraticOptimizer.h:52-96)
     def setVerbose(self, v): self.params.verbose = v
@@ -387,10 +388,12 @@ class QuadraticOptimizer:
     def setRTRInitialRadius(self, r): self.params.RTR_initial_radius = r
     def setRTRtCGIterations(self, n): self.params.RTR_tCG_iterations = n
 
-    def optimize(self, Y, active=None):
+    def optimize(self, Y, active=None, out=None):
+        """`out` may be Y itself (the solve is then in place)."""
         P = self.problem
         a = _Arg(Y, P.r, P.K)
-        out = _new_out(Y, P.r, P.K)
+        if out is None:
+            out = _new_out(Y, P.r, P.K)
         o = _Arg(out, P.r, P.K, out=True)
         res = (ROptResult * P.A)()
         prm = self.params.to_c()
@@ -400,11 +403,18 @@ class QuadraticOptimizer:
             assert act_arr.shape == (P.A,)
             act = act_arr.ctypes.data_as(_lib.c_uint8_p)
         check(P.lib.dcora_rtr_solve(P.h, a.ptr, o.ptr, C.byref(prm), act, res))
-        self.results = [ROPTResult(bool(x.success), x.fInit, x.gradNormInit, x.fOpt,
-                                   x.gradNormOpt, x.elapsedMs, x.tCGStatus,
-                                   x.outer_iterations, x.inner_iterations,
-                                   bool(x.accepted)) for x in res]
+        self._raw = res          # converted lazily: a batch holds hundreds of agents
+        self._results = None
         return out
+
+    @property
+    def results(self):
+        if self._results is None:
+            self._results = [ROPTResult(bool(x.success), x.fInit, x.gradNormInit, x.fOpt,
+                                        x.gradNormOpt, x.elapsedMs, x.tCGStatus,
+                                        x.outer_iterations, x.inner_iterations,
+                                        bool(x.accepted)) for x in self._raw]
+        return self._results
 
     def getOptResult(self):
         return self.results[0] if len(self.results) == 1 else self.results

@@ -143,6 +143,14 @@ scale_copy_kernel(const double *__restrict__ x, double s, double *__restrict__ y
   if (i < K) y[i] = s * x[i];
 }
 
+// out[i] = x[i * r + q]: row q of an r x K column-major matrix as a vector
+__global__ void __launch_bounds__(LZ_BLOCK)
+extract_row_kernel(const double *__restrict__ x, int r, int q, double *__restrict__ out,
+                   int64_t K) {
+  const int64_t i = (int64_t)blockIdx.x * LZ_BLOCK + threadIdx.x;
+  if (i < K) out[i] = x[i * r + q];
+}
+
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (host, tiny)
 void jacobi_eig(int n, std::vector<double> &Amat, std::vector<double> &evec,
                 std::vector<double> &eval) {
@@ -369,21 +377,115 @@ extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
                               p->stream));
     basis_rotate_kernel<<<gridK, LZ_BLOCK, sizeof(double) * m, p->stream>>>(V, K, m, 1, d_Y, w, K);
     p->launches += 1;
-    // theta = v^T S v (fastVerification :1727)
-    rc = apply_S(p, q1, Lam, w, tmp, basis[1 - cur]);
+    CERT_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  // Rayleigh-Ritz on span(rows of X).  At a critical point S X^T = 0, so the
+  // rows of X span (numerically) null vectors of S; the pencil's smallest
+  // eigenvalues are clustered there at a relative gap of ~1e-9 of the spectrum
+  // and a Krylov method from a random start resolves that cluster last.  Both
+  // numbers are Rayleigh quotients, i.e. upper bounds of lambda_min(S): report
+  // the smaller one (with its vector).
+  const int r = p->r;
+  if (2 * r <= m + 1) {
+    double *B = basis[1 - cur];            // r rows of X, then S * rows
+    const int gridr = gridK;
+    for (int q = 0; q < r; ++q) {
+      extract_row_kernel<<<gridr, LZ_BLOCK, 0, p->stream>>>(x, r, q, B + (size_t)q * K, K);
+      p->launches += 1;
+    }
+    std::vector<double> Mm((size_t)r * r), Nm((size_t)r * r), hh(LZ_MAXM);
+    for (int q = 0; q < r; ++q) {
+      double *SBq = B + (size_t)(r + q) * K;
+      rc = apply_S(p, q1, Lam, B + (size_t)q * K, tmp, SBq);
+      if (rc < 0) { cleanup(); return rc; }
+      ++matvecs;
+      for (int which = 0; which < 2; ++which) {
+        const double *rhs = which == 0 ? SBq : B + (size_t)q * K;
+        basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(B, K, r, rhs, K, d_part);
+        basis_dots_reduce_kernel<<<r, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, r, d_h);
+        p->launches += 2;
+        CERT_CUDA(cudaMemcpyAsync(hh.data(), d_h, sizeof(double) * r, cudaMemcpyDeviceToHost,
+                                  p->stream));
+        CERT_CUDA(cudaStreamSynchronize(p->stream));
+        for (int c = 0; c < r; ++c) (which == 0 ? Mm : Nm)[(size_t)c * r + q] = hh[c];
+      }
+    }
+    // generalised symmetric problem M y = mu N y.  N = X X^T is singular when
+    // the solution is rank deficient (the usual case above the optimal rank), so
+    // it is reduced with its own eigen-decomposition: N = U D U^T, basis
+    // W = U_k D_k^-1/2 over the numerically non-zero part, C = W^T M W.
+    std::vector<double> Ns((size_t)r * r), Un, Dn;
+    for (int i = 0; i < r; ++i)
+      for (int j2 = 0; j2 < r; ++j2)
+        Ns[(size_t)i * r + j2] = 0.5 * (Nm[(size_t)i * r + j2] + Nm[(size_t)j2 * r + i]);
+    jacobi_eig(r, Ns, Un, Dn);
+    double dmax = 0.0;
+    for (int i = 0; i < r; ++i) dmax = std::max(dmax, Dn[i]);
+    std::vector<int> keepc;
+    for (int i = 0; i < r; ++i)
+      if (Dn[i] > 1e-10 * dmax) keepc.push_back(i);
+    const int rk = (int)keepc.size();
+    if (rk > 0 && dmax > 0.0) {
+      // W[q][c] = U[q][keepc[c]] / sqrt(D[keepc[c]])
+      std::vector<double> Wn((size_t)r * rk);
+      for (int q = 0; q < r; ++q)
+        for (int c = 0; c < rk; ++c)
+          Wn[(size_t)q * rk + c] = Un[(size_t)q * r + keepc[c]] / std::sqrt(Dn[keepc[c]]);
+      std::vector<double> MW((size_t)r * rk, 0.0), Cm((size_t)rk * rk, 0.0);
+      for (int i = 0; i < r; ++i)
+        for (int c = 0; c < rk; ++c) {
+          double sacc = 0.0;
+          for (int t = 0; t < r; ++t)
+            sacc += 0.5 * (Mm[(size_t)i * r + t] + Mm[(size_t)t * r + i]) * Wn[(size_t)t * rk + c];
+          MW[(size_t)i * rk + c] = sacc;
+        }
+      for (int a2 = 0; a2 < rk; ++a2)
+        for (int c = 0; c < rk; ++c) {
+          double sacc = 0.0;
+          for (int t = 0; t < r; ++t) sacc += Wn[(size_t)t * rk + a2] * MW[(size_t)t * rk + c];
+          Cm[(size_t)a2 * rk + c] = sacc;
+        }
+      for (int a2 = 0; a2 < rk; ++a2)
+        for (int c = a2 + 1; c < rk; ++c) {
+          const double sym = 0.5 * (Cm[(size_t)a2 * rk + c] + Cm[(size_t)c * rk + a2]);
+          Cm[(size_t)a2 * rk + c] = sym;
+          Cm[(size_t)c * rk + a2] = sym;
+        }
+      std::vector<double> ev2, el2;
+      jacobi_eig(rk, Cm, ev2, el2);
+      int best = 0;
+      for (int i = 1; i < rk; ++i) if (el2[i] < el2[best]) best = i;
+      if (el2[best] < lam) {
+        lam = el2[best];
+        // coefficients on the rows of X: z = W y
+        std::vector<double> z(r, 0.0);
+        for (int q = 0; q < r; ++q)
+          for (int c = 0; c < rk; ++c) z[q] += Wn[(size_t)q * rk + c] * ev2[(size_t)c * rk + best];
+        CERT_CUDA(cudaMemcpyAsync(d_Y, z.data(), sizeof(double) * r, cudaMemcpyHostToDevice,
+                                  p->stream));
+        basis_rotate_kernel<<<gridK, LZ_BLOCK, sizeof(double) * r, p->stream>>>(B, K, r, 1, d_Y, w, K);
+        p->launches += 1;
+        CERT_CUDA(cudaStreamSynchronize(p->stream));
+      }
+    }
+  }
+  {
+    // theta = v^T S v (fastVerification :1727) and the residual ||S v - theta v||
+    double *Sw = basis[1 - cur];
+    rc = apply_S(p, q1, Lam, w, tmp, Sw);
     if (rc < 0) { cleanup(); return rc; }
-    basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(basis[1 - cur], K, 1, w, K, d_part);
-    basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
-    basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(w, K, 1, w, K, d_part + (size_t)nblk * 0);
-    p->launches += 2;
-    double vSv = 0.0;
-    CERT_CUDA(cudaMemcpyAsync(&vSv, d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    CERT_CUDA(cudaStreamSynchronize(p->stream));
-    basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
-    double vv = 1.0;
-    CERT_CUDA(cudaMemcpyAsync(&vv, d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    CERT_CUDA(cudaStreamSynchronize(p->stream));
+    double vals[3] = {0.0, 1.0, 0.0};
+    const double *lhs[3] = {Sw, w, Sw}, *rhs[3] = {w, w, Sw};
+    for (int t = 0; t < 3; ++t) {
+      basis_dots_kernel<<<nblk, LZ_BLOCK, 0, p->stream>>>(lhs[t], K, 1, rhs[t], K, d_part);
+      basis_dots_reduce_kernel<<<1, LZ_BLOCK, 0, p->stream>>>(d_part, nblk, 1, d_h);
+      p->launches += 2;
+      CERT_CUDA(cudaMemcpyAsync(&vals[t], d_h, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      CERT_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    const double vSv = vals[0], vv = vals[1], ss = vals[2];
     res->theta = vSv / vv;
+    resid = std::sqrt(std::max(0.0, ss / vv - res->theta * res->theta));
     if (v_out) {
       scale_copy_kernel<<<gridK, LZ_BLOCK, 0, p->stream>>>(w, 1.0 / std::sqrt(vv), tmp, K);
       rc = export_matrix(q1, tmp, v_out, 1);

@@ -9,7 +9,6 @@
 // loads/stores of X, V, OUT are coalesced, and the (d+1)x(d+1) Q blocks
 // (128 B for d=3) are read as one line per group.
 #include <cooperative_groups.h>
-#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -49,77 +48,12 @@ __device__ __forceinline__ bool agent_on(const int *flags, int agent, int mask_f
 }
 
 // ---------------------------------------------------------------- K1 SpMM
-// Wide read-only loads.  sm_100a has 256-bit global loads (LDG.E.256): a 3-D
-// pose block of X (r x 4 doubles, contiguous) is fetched with r*4/4 of them
-// instead of r*4 64-bit loads, which cuts the L1 sector traffic of the gather
-// 4x (the DH lanes of a pose read the same addresses; the request is merged).
-__device__ __forceinline__ void ldg_v4(const double *p, double &a, double &b, double &c,
-                                       double &d) {
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-// streaming variant for Q values (read once per product: do not allocate in L1)
-__device__ __forceinline__ void ldg_v4_stream(const double *p, double &a, double &b,
-                                              double &c, double &d) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-__device__ __forceinline__ void ldg_v2(const double *p, double &a, double &b) {
-  const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
-  a = v.x; b = v.y;
-}
-
-// xv[0..NB) = xb[0..NB) for xb at 8-byte offset OFF (in doubles) from a 32-byte
-// boundary: scalar / 128-bit prefix up to the boundary, 256-bit body, tail.
-template <int NB, int OFF>
-__device__ __forceinline__ void load_run(const double *xb, double (&xv)[NB]) {
-  constexpr int PRE0 = (4 - OFF) & 3;
-  constexpr int PRE = PRE0 < NB ? PRE0 : NB;
-  int i = 0;
-  if constexpr (PRE & 1) { xv[0] = __ldg(xb); i = 1; }
-  if constexpr (PRE >= 2) { ldg_v2(xb + (PRE & 1), xv[PRE & 1], xv[(PRE & 1) + 1]); i = PRE; }
-  constexpr int NV4 = (NB - PRE) / 4;
-#pragma unroll
-  for (int v = 0; v < NV4; ++v)
-    ldg_v4(xb + PRE + 4 * v, xv[PRE + 4 * v], xv[PRE + 4 * v + 1], xv[PRE + 4 * v + 2],
-           xv[PRE + 4 * v + 3]);
-  constexpr int T0 = PRE + 4 * NV4;
-  constexpr int REM = NB - T0;
-  if constexpr (REM >= 2) ldg_v2(xb + T0, xv[T0], xv[T0 + 1]);
-  if constexpr (REM & 1) xv[NB - 1] = __ldg(xb + NB - 1);
-  (void)i;
-}
-
-template <int NB>
-__device__ __forceinline__ void load_xblock(const double *xb, double (&xv)[NB]) {
-  const unsigned off = (unsigned)((reinterpret_cast<uintptr_t>(xb) >> 3) & 3u);
-  // uniform per agent (all pose blocks of an agent share the offset when
-  // R*DH is a multiple of 4), so this branch does not diverge in practice
-  if (off == 0) load_run<NB, 0>(xb, xv);
-  else if (off == 2) load_run<NB, 2>(xb, xv);
-  else if (off == 1) load_run<NB, 1>(xb, xv);
-  else load_run<NB, 3>(xb, xv);
-}
-
-template <int DH>
-__device__ __forceinline__ void load_qrow(const double *qp, double (&qv)[DH]) {
-  if constexpr (DH == 4) {
-    ldg_v4_stream(qp, qv[0], qv[1], qv[2], qv[3]);  // 32-byte aligned row of a 128-byte block
-  } else {
-#pragma unroll
-    for (int b = 0; b < DH; ++b) qv[b] = __ldcs(qp + b);
-  }
-}
-
 // Y[:, block i] = sum_j X[:, block j] * Q[j-block, i-block]  (+ G)
 // bval holds, for output block row i and input block j, the (d+1)x(d+1) block
 // [a][b] = Q[(j,b),(i,a)], row-major: lane a reads its row (DH contiguous
-// doubles; one 256-bit load for d=3), the DH lanes of a pose read the whole
-// 128-byte block.  The block column index and the Q row are fetched two
-// blocks ahead of their use (register ring), so that the DRAM latency of the
-// Q stream overlaps the dependent  bcol -> X gather  of the blocks before it.
-template <int R, int DH, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+// doubles; 32 B for d=3), the DH lanes of a pose read the whole 128-byte block.
+template <int R, int DH, int PF>
+__global__ void __launch_bounds__(128)
 bsr_spmm_kernel(int np, const int *__restrict__ browptr,
                 const int *__restrict__ bcol, const double *__restrict__ bval,
                 const int *__restrict__ prowcol, const int *__restrict__ pose_agent,
@@ -128,7 +62,6 @@ bsr_spmm_kernel(int np, const int *__restrict__ browptr,
                 const double *__restrict__ X, const double *__restrict__ G,
                 double *__restrict__ Y) {
   constexpr int PPW = Map<DH>::PPW;
-  constexpr int NB = R * DH;
   const int lane = threadIdx.x & 31;
   const int sub = lane / DH, a = lane - sub * DH;
   // a CTA covers 4*PPW consecutive pose rows: of the whole batch, or of one
@@ -148,29 +81,33 @@ bsr_spmm_kernel(int np, const int *__restrict__ browptr,
 #pragma unroll
   for (int q = 0; q < R; ++q) acc[q] = 0.0;
   const int p0 = browptr[i], p1 = browptr[i + 1];
-  const double *qbase = bval + (size_t)a * DH;
-  int c0 = 0, c1 = 0;
-  double q0[DH], q1[DH];
-#pragma unroll
-  for (int b = 0; b < DH; ++b) { q0[b] = 0.0; q1[b] = 0.0; }
-  if (p0 < p1) { c0 = __ldg(bcol + p0); load_qrow<DH>(qbase + (size_t)p0 * (DH * DH), q0); }
-  if (p0 + 1 < p1) { c1 = __ldg(bcol + p0 + 1); load_qrow<DH>(qbase + (size_t)(p0 + 1) * (DH * DH), q1); }
+  // PF: the block column index is fetched one block ahead, so the X gather of
+  // a block does not wait for a dependent index load
+  int cnext = (PF && p0 < p1) ? __ldg(bcol + p0) : 0;
   for (int p = p0; p < p1; ++p) {
-    double xv[NB];
-    load_xblock<NB>(X + (size_t)c0 * R, xv);
-    int c2 = 0;
-    double q2[DH];
+    int c;
+    if (PF) {
+      c = cnext;
+      if (p + 1 < p1) cnext = __ldg(bcol + p + 1);
+    } else {
+      c = __ldg(bcol + p);
+    }
+    const double *qp = bval + (size_t)p * (DH * DH) + a * DH;
+    double qv[DH];
+    if (DH == 4) {
+      const double2 q01 = __ldg(reinterpret_cast<const double2 *>(qp));
+      const double2 q23 = __ldg(reinterpret_cast<const double2 *>(qp) + 1);
+      qv[0] = q01.x; qv[1] = q01.y; qv[2] = q23.x; qv[DH - 1] = q23.y;
+    } else {
 #pragma unroll
-    for (int b = 0; b < DH; ++b) q2[b] = 0.0;
-    if (p + 2 < p1) { c2 = __ldg(bcol + p + 2); load_qrow<DH>(qbase + (size_t)(p + 2) * (DH * DH), q2); }
+      for (int b = 0; b < DH; ++b) qv[b] = __ldg(qp + b);
+    }
+    const double *xj = X + (size_t)c * R;
 #pragma unroll
     for (int b = 0; b < DH; ++b) {
 #pragma unroll
-      for (int q = 0; q < R; ++q) acc[q] = fma(q0[b], xv[b * R + q], acc[q]);
+      for (int q = 0; q < R; ++q) acc[q] = fma(qv[b], __ldg(xj + b * R + q), acc[q]);
     }
-    c0 = c1; c1 = c2;
-#pragma unroll
-    for (int b = 0; b < DH; ++b) { q0[b] = q1[b]; q1[b] = q2[b]; }
   }
   const size_t o = (size_t)(prowcol[i] + a) * R;
   if (G != nullptr) {
@@ -613,22 +550,11 @@ int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
   const ActiveSet *as = active_set(p, mask_flag);
   if (A.np > 0 && (!as || as->n_tiles > 0)) {
     DCORA_DISPATCH_RD(p->r, M.d, {
-      constexpr int PPW = Map<DH>::PPW;
-      const int ppc = 4 * PPW;
+      const int ppc = spmm_rows_per_cta(M.d);
       const int grid = as ? as->n_tiles : (A.np + ppc - 1) / ppc;
-      static const int variant = getenv("DCORA_SPMM_MINB") ? atoi(getenv("DCORA_SPMM_MINB")) : 5;
-      if (variant >= 8)
-        bsr_spmm_kernel<R, DH, 8><<<grid, 128, 0, p->stream>>>(
-            A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
-            mask_flag, as ? as->tiles : nullptr, X, G, Y);
-      else if (variant >= 6)
-        bsr_spmm_kernel<R, DH, 6><<<grid, 128, 0, p->stream>>>(
-            A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
-            mask_flag, as ? as->tiles : nullptr, X, G, Y);
-      else
-        bsr_spmm_kernel<R, DH, 5><<<grid, 128, 0, p->stream>>>(
-            A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
-            mask_flag, as ? as->tiles : nullptr, X, G, Y);
+      bsr_spmm_kernel<R, DH, 0><<<grid, 128, 0, p->stream>>>(
+          A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
+          mask_flag, as ? as->tiles : nullptr, X, G, Y);
     })
     DCORA_LAUNCH_CHECK(p);
   }

@@ -91,7 +91,7 @@ int trsv_warps_per_cta();
 // workspace vector indices (p->vec(i))
 enum Ws : int {
   WS_X1 = 0, WS_X2, WS_EG, WS_GF, WS_S, WS_ETA, WS_DELTA, WS_HD, WS_R, WS_Z,
-  WS_T0, WS_T1, WS_TRSV_PANEL, WS_TRSV_TMP, WS_TRSV_SOL, WS_IO0, WS_IO1, WS_IO2, WS_COUNT
+  WS_T0, WS_T1, WS_HETA, WS_TRSV_PANEL, WS_TRSV_TMP, WS_TRSV_SOL, WS_IO0, WS_IO1, WS_IO2, WS_COUNT
 };
 
 }  // namespace dcora
@@ -118,6 +118,9 @@ enum Ws : int {
       set_error("rank outside 1..16");                     \
       return DCORA_ERR_ARG;                                \
   }
+
+// K1: pose rows per CTA (the active-set tiles are built to match)
+inline int spmm_rows_per_cta(int d) { return 4 * (32 / (d + 1)); }
 
 #define DCORA_DISPATCH_RD(r, d, ...)                       \
   if ((d) == 3) { constexpr int DH = 4; DCORA_DISPATCH_R(r, __VA_ARGS__) } \

@@ -12,6 +12,8 @@
 // kernels are masked per agent, so agents converge independently while sharing
 // launches.  The host only reads back two counters per iteration.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 
 #include "solver.cuh"
@@ -279,10 +281,19 @@ static int rhess(dcora_problem *p, const double *x1, const double *S, const doub
   return launch_rhess_correct(p, x1, S, v, tmp, out, mask);
 }
 
-// EG, gf, S at x1 for the agents selected by `mask`; leaves <gf,gf> in partial 0
+// EG, gf, S at x1 for the agents selected by `mask`; leaves <gf,gf> in partial 0.
+// `XQ` (optional) holds x1*Q from the cost evaluation at the same point
+// (eval_f): the Euclidean gradient is then XQ + G, bit-identical to the fused
+// SpMM epilogue, without a second pass over Q.
 static int gradient_at(dcora_problem *p, const double *x1, double *EG, double *gf,
-                       double *S, int mask) {
-  DCORA_TRY(launch_spmm(p, x1, p->has_G ? p->G : nullptr, EG, mask));
+                       double *S, int mask, const double *XQ = nullptr) {
+  if (XQ == nullptr) {
+    DCORA_TRY(launch_spmm(p, x1, p->has_G ? p->G : nullptr, EG, mask));
+  } else if (p->has_G) {
+    DCORA_TRY(launch_axpby(p, EG, -1, 1.0, XQ, -1, 1.0, p->G, mask));
+  } else {
+    DCORA_TRY(launch_copy(p, EG, XQ, mask));
+  }
   DCORA_TRY(launch_project_tangent(p, x1, EG, gf, mask));
   DCORA_TRY(launch_sym_ytg(p, x1, EG, S, mask));
   const double *xs[1] = {gf};
@@ -328,7 +339,7 @@ int set_user_mask(dcora_problem *p, const uint8_t *active) {
       std::vector<int> agents, chunks, rem, crem;
       std::vector<int2> tiles;
       std::vector<uint8_t> mask(active, active + A);
-      const int ppc = 4 * (32 / (M.d + 1));
+      const int ppc = spmm_rows_per_cta(M.d);
       for (int a = 0; a < A; ++a) {
         if (!active[a]) continue;
         agents.push_back(a);
@@ -363,15 +374,45 @@ int set_user_mask(dcora_problem *p, const uint8_t *active) {
   return DCORA_OK;
 }
 
+namespace {
+// DCORA_TIMING=1: wall-clock split of one rtr_solve into its phases (adds a
+// stream synchronise per mark: profiling aid only, never on in benchmarks).
+struct PhaseTimer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  explicit PhaseTimer(cudaStream_t s) : on(getenv("DCORA_TIMING") != nullptr), st(s) {
+    if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); }
+  }
+  void mark(int slot) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    acc[slot] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report(int outer, int inner) {
+    if (!on) return;
+    fprintf(stderr, "[dcora timing] init %.0f | tcg-setup(precond) %.0f | tcg-iter(spmm..stepB) %.0f | "
+                    "tcg-iter(precond..) %.0f | candidate+rho %.0f | accept+grad %.0f | readback %.0f us"
+                    "  (outer %d, tcg %d)\n",
+            acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], outer, inner);
+  }
+};
+}  // namespace
+
 int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
                      const uint8_t *active, dcora_ropt_result *results) {
   DeviceMatrices &M = *p->M;
+  PhaseTimer pt(p->stream);
+  int n_outer_done = 0, n_inner_done = 0;
   const int A = M.A;
   double *x2 = p->vec(WS_X2), *EG = p->vec(WS_EG), *gf = p->vec(WS_GF);
   double *S = p->vec(WS_S), *eta = p->vec(WS_ETA), *delta = p->vec(WS_DELTA);
   double *Hd = p->vec(WS_HD), *r = p->vec(WS_R), *z = p->vec(WS_Z);
-  double *t0 = p->vec(WS_T0);
-  if (!x2 || !EG || !gf || !S || !eta || !delta || !Hd || !r || !z || !t0)
+  double *t0 = p->vec(WS_T0), *xq = p->vec(WS_T1), *Heta = p->vec(WS_HETA);
+  if (!x2 || !EG || !gf || !S || !eta || !delta || !Hd || !r || !z || !t0 || !xq || !Heta)
     return DCORA_ERR_ALLOC;
   int *counters = p->flags + (size_t)NF * A;
   const auto tstart = std::chrono::steady_clock::now();
@@ -387,8 +428,8 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   }
 
   // initial statistics: fInit, gradNormInit (QuadraticOptimizer.cpp:30-31)
-  DCORA_TRY(eval_f(p, x1, t0, S_F1, F_USER));
-  DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER));
+  DCORA_TRY(eval_f(p, x1, xq, S_F1, F_USER));
+  DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER, xq));
   DCORA_TRY(zero_counter(p, 0));
   const int single_mode = prm->RTR_iterations == 1;
   const int max_outer = single_mode ? 12 : prm->RTR_iterations;
@@ -401,6 +442,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   int cnt[2];
   DCORA_TRY(read_counters(p, cnt));
   int n_outer = cnt[0];
+  pt.mark(0);
 
   if (prm->method == 1) {
     // one Riemannian gradient-descent step (QuadraticOptimizer.cpp:124-201)
@@ -419,6 +461,9 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     // ---- tCG (SolversTR::tCG_TR), eta0 = 0
     DCORA_TRY(launch_copy(p, r, gf, F_OUTER));
     DCORA_TRY(launch_axpby(p, eta, -1, 0.0, gf, -1, 0.0, nullptr, F_OUTER));
+    // H eta is accumulated with eta (H eta += c H delta, the Hessian is linear on the
+    // tangent space), which saves the SpMM of a separate H*eta for the model decrease
+    DCORA_TRY(launch_axpby(p, Heta, -1, 0.0, gf, -1, 0.0, nullptr, F_OUTER));
     DCORA_TRY(launch_precond(p, x1, r, z, F_OUTER));
     {
       const double *xs[1] = {z}, *ys[1] = {r};
@@ -428,6 +473,8 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, -1, 0.0, nullptr, F_TCG));
     int n_tcg = n_outer;
+    pt.mark(1);
+    ++n_outer_done;
     for (int j = 0; j < prm->RTR_tCG_iterations && n_tcg > 0; ++j) {
       DCORA_TRY(rhess(p, x1, S, delta, t0, Hd, F_TCG));
       {
@@ -437,6 +484,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       tcg_stepA_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       DCORA_TRY(launch_axpby(p, eta, -1, 1.0, eta, S_CETA, 1.0, delta, F_STEP));
+      DCORA_TRY(launch_axpby(p, Heta, -1, 1.0, Heta, S_CETA, 1.0, Hd, F_STEP));
       DCORA_TRY(launch_axpby(p, r, -1, 1.0, r, S_CR, 1.0, Hd, F_STEP));
       {
         const double *xs[1] = {r};
@@ -447,6 +495,8 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
                                                  p->scal, j, 0, prm->RTR_tCG_iterations,
                                                  counters);
       DCORA_LAUNCH_CHECK(p);
+      pt.mark(2);
+      ++n_inner_done;
       DCORA_TRY(launch_precond(p, x1, r, z, F_TCG));
       {
         const double *xs[1] = {z}, *ys[1] = {r};
@@ -458,26 +508,28 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, S_BETA, 1.0, delta, F_TCG));
       DCORA_TRY(read_counters(p, cnt));
       n_tcg = cnt[1];
+      pt.mark(3);
     }
     // ---- candidate, model decrease, rho (SolversTR::Run)
     DCORA_TRY(launch_retract(p, x1, eta, x2, prm->retraction, F_OUTER));
-    DCORA_TRY(eval_f(p, x2, t0, S_F2, F_OUTER));
-    DCORA_TRY(rhess(p, x1, S, eta, t0, Hd, F_OUTER));
+    DCORA_TRY(eval_f(p, x2, xq, S_F2, F_OUTER));  // xq = x2*Q, reused by the gradient
     {
-      const double *xs[2] = {eta, eta}, *ys[2] = {gf, Hd};
+      const double *xs[2] = {eta, eta}, *ys[2] = {gf, Heta};
       DCORA_TRY(launch_dots(p, 2, xs, ys, F_OUTER));
     }
     rtr_rho_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
                                              single_mode);
     DCORA_LAUNCH_CHECK(p);
+    pt.mark(4);
     DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));
-    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT));
+    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT, xq));
     DCORA_TRY(zero_counter(p, 0));
     rtr_accept_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
                                                 max_outer, single_mode, counters);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(read_counters(p, cnt));
     n_outer = cnt[0];
+    pt.mark(5);
     if (prm->time_bound_s > 0.0) {
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count();
       if (el > prm->time_bound_s) break;
@@ -486,12 +538,14 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
 
   if (prm->method == 1) {
     // statistics after the RGD step
-    DCORA_TRY(eval_f(p, x1, t0, S_F1, F_USER));
-    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER));
+    DCORA_TRY(eval_f(p, x1, xq, S_F1, F_USER));
+    DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER, xq));
     const int dst[1] = {S_TMP0};
     DCORA_TRY(launch_reduce_scalars(p, 1, dst));
   }
   DCORA_TRY(read_scalars(p));
+  pt.mark(6);
+  pt.report(n_outer_done, n_inner_done);
   const double ms =
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tstart).count();
   if (results) {

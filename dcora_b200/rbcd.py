@@ -214,7 +214,7 @@ class RBCD:
             self.exchange()
             if active.any():
                 self.P.update_G(self.X, self.H, active)
-                self.X = self.opt.optimize(self.X, active)
+                self.X = self.opt.optimize(self.X, active, out=self.X)
                 self.agent_updates += int(active.sum())
 
     def monitor(self):

@@ -153,3 +153,19 @@ def test_batched_agents_match_individual_solves():
     Xm = ob.optimize(np.concatenate(X0s, axis=1), active=[0, 1, 0])
     assert np.array_equal(Xm[:, :Ps[0].L.k], X0s[0])
     assert not np.array_equal(Xm[:, Ps[0].L.k:Ps[0].L.k + Ps[1].L.k], X0s[1])
+
+
+def test_staircase_driver_escapes_the_saddle_and_certifies():
+    # rank-3 start that converges to a saddle (see test_saddle_is_detected_and_escaped):
+    # the staircase driver must climb and end at the certified optimum
+    import dcora_b200 as dc
+    from dcora_b200.staircase import riemannian_staircase
+    P3, g, info = central_problem("smallGrid3D", 3)
+    gp3 = gpu_problem(P3)
+    X0 = mf.random_point(P3.L, np.random.default_rng(7))
+    res = riemannian_staircase(gp3, X0, r_max=8, eta=1e-3)
+    assert res.certified and res.lambda_min > -1e-3
+    assert abs(2 * res.cost - 1025.3980521) < 1e-5
+    assert res.levels[0]["r"] == 3
+    if len(res.levels) > 1:
+        assert not res.levels[0]["is_psd"] and res.levels[-1]["f"] < res.levels[0]["f"]

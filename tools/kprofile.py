@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--rbcd-steps", type=int, default=0, help="RBCD iterations to run first")
+    ap.add_argument("--split", action="store_true", help="per-colour wall-clock split of a sweep")
     ap.add_argument("kinds", nargs="*", default=["spmm", "precond"])
     a = ap.parse_args()
     import dcora_b200 as dc
@@ -29,6 +30,21 @@ def main():
     for _ in range(a.rbcd_steps):
         t0 = time.perf_counter(); S.iterate(); torch.cuda.synchronize()
         log(f"rbcd step {1e3 * (time.perf_counter() - t0):.1f} ms")
+    if a.split:
+        # wall-clock split of one sweep per colour (synchronised: profiling aid)
+        import numpy as np
+        for c in range(S.plan.num_colors):
+            act = (S.local_colors == c).astype(np.uint8)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            S.exchange(); S.P.update_G(S.X, S.H, act)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            S.X = S.opt.optimize(S.X, act)
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+            log(f"colour {c}: {int(act.sum())} agents  update_G {1e3 * (t1 - t0):.2f} ms  "
+                f"optimize {1e3 * (t2 - t1):.2f} ms")
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        S.monitor(); torch.cuda.synchronize()
+        log(f"monitor {1e3 * (time.perf_counter() - t0):.2f} ms")
     peak, _ = bench.peaks()
     for kind in a.kinds:
         ms, by = S.P.time_kernel(kind, a.iters)
