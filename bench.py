@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-agents", type=int, default=2)
     ap.add_argument("--kernel-iters", type=int, default=20)
+    ap.add_argument("--ttc-grid", type=int, default=12,
+                    help="side of the single-agent grid of the time-to-certified leg (0: skip)")
     return ap.parse_args()
 
 
@@ -64,6 +66,21 @@ def peaks():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def k1_traffic(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one full-batch K1 launch on the default
+    workload, from the committed ncu --set full capture (profiles/k1_traffic.json); null for
+    any other workload / GPU count (no capture)."""
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if world != 1 or (args.grid, args.agents, args.rank, args.range_fraction) != (100, 256, 5, 0.1):
+        return None
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -269,6 +286,22 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args, gp, S, X0, log)
 
+    # ---- time-to-certified-solution (BASELINE.json metric, second half): single-agent
+    #      Riemannian staircase + certificate on a small range-aided grid, everything counted
+    #      (assembly, Cholesky + tape build + upload, solve, certification)
+    ttc = None
+    if rank == 0 and args.ttc_grid > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ttc as ttc_mod
+            ttc = ttc_mod.run(args.ttc_grid, args.rank, args.range_fraction, args.seed)
+            ttc.pop("levels", None)
+            log(f"time-to-certified ({ttc['poses']} poses): {ttc['seconds']:.2f} s "
+                f"(setup {ttc['factor_upload_s']:.2f} s, solve+certify {ttc['solve_certify_s']:.2f} s), "
+                f"certified={ttc['certified']} rank={ttc['rank']}")
+        except Exception as e:  # pragma: no cover
+            ttc = {"error": repr(e)}
+
     if rank == 0:
         out = {
             "metric": "RBCD iterations/s",
@@ -302,12 +335,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "bsr_spmm_kernel (Q-SpMM, K1)", "bound": "hbm",
                          "achieved": kern["spmm"]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kern["spmm"]["frac"], "traffic": None,
+                         "frac": kern["spmm"]["frac"], "traffic": k1_traffic(args, world),
                          "peak_source": peak_src,
                          "algorithmic_bytes": kern["spmm"]["bytes"],
                          "launch_ms": kern["spmm"]["ms"]},
             "kernels": kern,
         }
+        if ttc is not None:
+            out["time_to_certified"] = ttc
         if e2e is not None:
             out["e2e"] = e2e
         if cpu is not None:

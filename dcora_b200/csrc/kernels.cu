@@ -49,10 +49,14 @@ __device__ __forceinline__ bool agent_on(const int *flags, int agent, int mask_f
 
 // ---------------------------------------------------------------- K1 SpMM
 // Y[:, block i] = sum_j X[:, block j] * Q[j-block, i-block]  (+ G)
+// (Round-1 variant study -- wide 128/256-bit loads, register and cp.async
+// software pipelines, streaming several rows per lane group -- is recorded in
+// profiles/experiments/r01_k1_variants.md: every variant lost to this plain
+// gather loop, which keeps 40 warps per SM resident at 48 registers.)
 // bval holds, for output block row i and input block j, the (d+1)x(d+1) block
 // [a][b] = Q[(j,b),(i,a)], row-major: lane a reads its row (DH contiguous
 // doubles; 32 B for d=3), the DH lanes of a pose read the whole 128-byte block.
-template <int R, int DH, int PF>
+template <int R, int DH>
 __global__ void __launch_bounds__(128)
 bsr_spmm_kernel(int np, const int *__restrict__ browptr,
                 const int *__restrict__ bcol, const double *__restrict__ bval,
@@ -81,17 +85,8 @@ bsr_spmm_kernel(int np, const int *__restrict__ browptr,
 #pragma unroll
   for (int q = 0; q < R; ++q) acc[q] = 0.0;
   const int p0 = browptr[i], p1 = browptr[i + 1];
-  // PF: the block column index is fetched one block ahead, so the X gather of
-  // a block does not wait for a dependent index load
-  int cnext = (PF && p0 < p1) ? __ldg(bcol + p0) : 0;
   for (int p = p0; p < p1; ++p) {
-    int c;
-    if (PF) {
-      c = cnext;
-      if (p + 1 < p1) cnext = __ldg(bcol + p + 1);
-    } else {
-      c = __ldg(bcol + p);
-    }
+    const int c = __ldg(bcol + p);
     const double *qp = bval + (size_t)p * (DH * DH) + a * DH;
     double qv[DH];
     if (DH == 4) {
@@ -309,7 +304,8 @@ enum ManifoldOp : int {
   OP_SYM,           // S = sym(Y^T EG)
   OP_RETRACT_QF,    // OUT = qf(X + V)
   OP_RETRACT_POLAR, // OUT = polar(X + V)
-  OP_PROJ_MANIFOLD  // OUT = polar(M) / normalised
+  OP_PROJ_MANIFOLD, // OUT = polar(M) / normalised
+  OP_GRAD           // AUX = EG = V + HV(G); OUT = proj_X(EG); S = sym(Y^T EG)
 };
 
 template <int R, int DH, int OP>
@@ -317,11 +313,18 @@ __global__ void __launch_bounds__(128)
 manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
                 int mask_flag, const int *__restrict__ list, const double *__restrict__ X,
                 const double *__restrict__ V, const double *__restrict__ HV,
-                const double *__restrict__ S, double *__restrict__ OUT) {
+                const double *S, double *__restrict__ OUT,
+                double *__restrict__ AUX, double *__restrict__ partials) {
+  // `partials` (optional, OP_RHESS / OP_GRAD): the chunk's share of <V, OUT>
+  // (OP_RHESS: <delta, H delta>) or <OUT, OUT> (OP_GRAD: <gf, gf>) goes to
+  // partial slot 0 -- the fused form of a following dots_kernel launch.
   constexpr int D = DH - 1;
   constexpr int PPW = Map<DH>::PPW;
-  const Chunk ch = chunks[list ? list[blockIdx.x] : blockIdx.x];
+  __shared__ double red_sm[4];
+  const int cid = list ? list[blockIdx.x] : blockIdx.x;
+  const Chunk ch = chunks[cid];
   if (!agent_on(flags, ch.agent, mask_flag)) return;
+  double dsum = 0.0;
   if (ch.kind == KIND_POSE) {
     const int nposes = ch.ncols / DH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -353,7 +356,19 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
           for (int q = 0; q < R; ++q) OUT[o + q] = V[o + q];
         } else if (OP == OP_RHESS) {
 #pragma unroll
-          for (int q = 0; q < R; ++q) OUT[o + q] = HV[o + q];
+          for (int q = 0; q < R; ++q) {
+            const double h = HV[o + q];
+            OUT[o + q] = h;
+            dsum = fma(V[o + q], h, dsum);
+          }
+        } else if (OP == OP_GRAD) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const double e = HV ? V[o + q] + HV[o + q] : V[o + q];
+            AUX[o + q] = e;
+            OUT[o + q] = e;
+            dsum = fma(e, e, dsum);
+          }
         } else if (OP == OP_PROJ_MANIFOLD) {
 #pragma unroll
           for (int q = 0; q < R; ++q) OUT[o + q] = X[o + q];
@@ -366,7 +381,31 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
       double Yb[D][R];
       load_block<R, D>(X + pb, Yb);
       double out[R];
-      if (OP == OP_PROJECT) {
+      if (OP == OP_GRAD) {
+        double Gb[D][R];
+        load_block<R, D>(V + pb, Gb);
+        if (HV != nullptr) {
+#pragma unroll
+          for (int b = 0; b < D; ++b)
+#pragma unroll
+            for (int q = 0; q < R; ++q) Gb[b][q] += HV[pb + b * R + q];
+        }
+        stiefel_proj_col<R, D>(Yb, Gb, a, out);
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+          double sv = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; ++c)
+            if (c == a) {
+              sv = 0.5 * (dotR<R>(Yb[b], Gb[c]) + dotR<R>(Yb[c], Gb[b]));
+#pragma unroll
+              for (int q = 0; q < R; ++q) if (b == 0) AUX[o + q] = Gb[c][q];
+            }
+          const_cast<double *>(S)[pb + a * D + b] = sv;  // S[b][a] (symmetric)
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) dsum = fma(out[q], out[q], dsum);
+      } else if (OP == OP_PROJECT) {
         double Vb[D][R];
         load_block<R, D>(V + pb, Vb);
         stiefel_proj_col<R, D>(Yb, Vb, a, out);
@@ -387,6 +426,8 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
 #pragma unroll
             for (int q = 0; q < R; ++q) Wb[c][q] = fma(-Sm[b][c], Vb[b][q], Wb[c][q]);
         stiefel_proj_col<R, D>(Yb, Wb, a, out);
+#pragma unroll
+        for (int q = 0; q < R; ++q) dsum = fma(V[o + q], out[q], dsum);
       } else if (OP == OP_PROJ_MANIFOLD) {
         polar_block<R, D>(Yb);
 #pragma unroll
@@ -414,8 +455,7 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
 #pragma unroll
       for (int q = 0; q < R; ++q) OUT[o + q] = out[q];
     }
-    return;
-  }
+  } else {
   // unit-sphere (oblique) and Euclidean (landmark) columns: one thread each
   for (int c = threadIdx.x; c < ch.ncols; c += 128) {
     const size_t o = (size_t)(ch.col0 + c) * R;
@@ -425,7 +465,12 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
       for (int q = 0; q < R; ++q) {
         double v;
         if (OP == OP_PROJECT) v = V[o + q];
-        else if (OP == OP_RHESS) v = HV[o + q];
+        else if (OP == OP_RHESS) { v = HV[o + q]; dsum = fma(V[o + q], v, dsum); }
+        else if (OP == OP_GRAD) {
+          v = HV ? V[o + q] + HV[o + q] : V[o + q];
+          AUX[o + q] = v;
+          dsum = fma(v, v, dsum);
+        }
         else if (OP == OP_PROJ_MANIFOLD) v = X[o + q];
         else v = X[o + q] + V[o + q];
         OUT[o + q] = v;
@@ -440,6 +485,21 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
 #pragma unroll
       for (int q = 0; q < R; ++q) g[q] = V[o + q];
       OUT[o] = dotR<R>(y, g);
+    } else if (OP == OP_GRAD) {
+      double g[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        g[q] = HV ? V[o + q] + HV[o + q] : V[o + q];
+        AUX[o + q] = g[q];
+      }
+      const double t = dotR<R>(y, g);
+      const_cast<double *>(S)[o] = t;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double gq = fma(-t, y[q], g[q]);
+        OUT[o + q] = gq;
+        dsum = fma(gq, gq, dsum);
+      }
     } else if (OP == OP_PROJECT || OP == OP_RHESS) {
       double w[R];
       if (OP == OP_PROJECT) {
@@ -452,7 +512,11 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
       }
       const double t = dotR<R>(y, w);  // v - y (y^T v), DCORA_utils.cpp:2043-2051
 #pragma unroll
-      for (int q = 0; q < R; ++q) OUT[o + q] = fma(-t, y[q], w[q]);
+      for (int q = 0; q < R; ++q) {
+        const double oq = fma(-t, y[q], w[q]);
+        OUT[o + q] = oq;
+        if (OP == OP_RHESS) dsum = fma(V[o + q], oq, dsum);
+      }
     } else {
       if (OP != OP_PROJ_MANIFOLD) {
 #pragma unroll
@@ -462,6 +526,11 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
 #pragma unroll
       for (int q = 0; q < R; ++q) OUT[o + q] = y[q] * inv;
     }
+  }
+  }
+  if ((OP == OP_RHESS || OP == OP_GRAD) && partials != nullptr) {
+    const double t = block_sum<128>(dsum, red_sm);
+    if (threadIdx.x == 0) partials[(size_t)cid * NPART + 0] = t;
   }
 }
 
@@ -510,6 +579,52 @@ axpby_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
   }
 }
 
+// tCG start: r = gf, eta = 0, Heta = 0 in one pass
+__global__ void __launch_bounds__(128)
+tcg_begin_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
+                 int mask_flag, const int *__restrict__ list, int R,
+                 const double *__restrict__ gf, double *__restrict__ r,
+                 double *__restrict__ eta, double *__restrict__ Heta) {
+  const Chunk ch = chunks[list ? list[blockIdx.x] : blockIdx.x];
+  if (!agent_on(flags, ch.agent, mask_flag)) return;
+  const size_t o = (size_t)ch.col0 * R;
+  const int len = ch.ncols * R;
+  for (int i = threadIdx.x; i < len; i += 128) {
+    r[o + i] = gf[o + i];
+    eta[o + i] = 0.0;
+    Heta[o + i] = 0.0;
+  }
+}
+
+// tCG step: eta += c_eta delta, Heta += c_eta Hd, r += c_r Hd, partial 0 = <r, r>
+// (c_eta = scal[S_CETA], c_r = scal[S_CR] of the agent)
+__global__ void __launch_bounds__(128)
+tcg_update_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
+                  int mask_flag, const int *__restrict__ list, int R,
+                  const double *__restrict__ scal, int slot_eta, int slot_r,
+                  const double *__restrict__ delta, const double *__restrict__ Hd,
+                  double *__restrict__ eta, double *__restrict__ Heta, double *__restrict__ r,
+                  double *__restrict__ partials) {
+  __shared__ double sm[4];
+  const int cid = list ? list[blockIdx.x] : blockIdx.x;
+  const Chunk ch = chunks[cid];
+  if (!agent_on(flags, ch.agent, mask_flag)) return;
+  const double ce = scal[ch.agent * NS + slot_eta], cr = scal[ch.agent * NS + slot_r];
+  const size_t o = (size_t)ch.col0 * R;
+  const int len = ch.ncols * R;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < len; i += 128) {
+    const double h = Hd[o + i];
+    eta[o + i] = fma(1.0, eta[o + i], ce * delta[o + i]);
+    Heta[o + i] = fma(1.0, Heta[o + i], ce * h);
+    const double rn = fma(1.0, r[o + i], cr * h);
+    r[o + i] = rn;
+    acc = fma(rn, rn, acc);
+  }
+  const double t = block_sum<128>(acc, sm);
+  if (threadIdx.x == 0) partials[(size_t)cid * NPART + 0] = t;
+}
+
 // reference <-> internal column permutation (gather)
 __global__ void __launch_bounds__(256)
 permute_kernel(int64_t K, int R, const int *__restrict__ perm,
@@ -552,7 +667,7 @@ int launch_spmm_mat(dcora_problem *p, const SpmmMat &A, const double *X,
     DCORA_DISPATCH_RD(p->r, M.d, {
       const int ppc = spmm_rows_per_cta(M.d);
       const int grid = as ? as->n_tiles : (A.np + ppc - 1) / ppc;
-      bsr_spmm_kernel<R, DH, 0><<<grid, 128, 0, p->stream>>>(
+      bsr_spmm_kernel<R, DH><<<grid, 128, 0, p->stream>>>(
           A.np, A.browptr, A.bcol, A.bval, A.prowcol, A.pose_agent, p->flags,
           mask_flag, as ? as->tiles : nullptr, X, G, Y);
     })
@@ -587,7 +702,7 @@ int launch_spmm(dcora_problem *p, const double *X, const double *G, double *Y,
 template <int OP>
 static int launch_manifold(dcora_problem *p, const double *X, const double *V,
                            const double *HV, const double *S, double *OUT,
-                           int mask_flag) {
+                           int mask_flag, double *AUX = nullptr, double *partials = nullptr) {
   DeviceMatrices &M = *p->M;
   if (M.nchunks == 0) return DCORA_OK;
   const ActiveSet *as = active_set(p, mask_flag);
@@ -598,7 +713,8 @@ static int launch_manifold(dcora_problem *p, const double *X, const double *V,
       return DCORA_ERR_ARG;
     }
     manifold_kernel<R, DH, OP><<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
-        M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, X, V, HV, S, OUT);
+        M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, X, V, HV, S, OUT, AUX,
+        partials);
   })
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
@@ -610,8 +726,16 @@ int launch_project_tangent(dcora_problem *p, const double *X, const double *V,
 }
 int launch_rhess_correct(dcora_problem *p, const double *X, const double *S,
                          const double *V, const double *HV, double *OUT,
-                         int mask_flag) {
-  return launch_manifold<OP_RHESS>(p, X, V, HV, S, OUT, mask_flag);
+                         int mask_flag, bool with_dot) {
+  return launch_manifold<OP_RHESS>(p, X, V, HV, S, OUT, mask_flag, nullptr,
+                                   with_dot ? p->partials : nullptr);
+}
+// EG = XQ + G, gf = proj_X(EG), S = sym(X^T EG), partial 0 = <gf, gf>: the
+// gradient stage of RTR in one pass (replaces axpby + project + sym + dots)
+int launch_gradient_fused(dcora_problem *p, const double *X, const double *XQ,
+                          const double *G, double *EG, double *gf, double *S,
+                          int mask_flag) {
+  return launch_manifold<OP_GRAD>(p, X, XQ, G, S, gf, mask_flag, EG, p->partials);
 }
 int launch_sym_ytg(dcora_problem *p, const double *X, const double *EG, double *S,
                    int mask_flag) {
@@ -651,6 +775,29 @@ int launch_axpby(dcora_problem *p, double *out, int slot_a, double ca,
   axpby_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
       M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r, p->scal, slot_a, ca, x,
       slot_b, cb, y, out);
+  DCORA_LAUNCH_CHECK(p);
+  return DCORA_OK;
+}
+
+int launch_tcg_begin(dcora_problem *p, const double *gf, double *r, double *eta, double *Heta,
+                     int mask_flag) {
+  DeviceMatrices &M = *p->M;
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
+  tcg_begin_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+      M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r, gf, r, eta, Heta);
+  DCORA_LAUNCH_CHECK(p);
+  return DCORA_OK;
+}
+
+int launch_tcg_update(dcora_problem *p, int slot_eta, int slot_r, const double *delta,
+                      const double *Hd, double *eta, double *Heta, double *r, int mask_flag) {
+  DeviceMatrices &M = *p->M;
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
+  tcg_update_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+      M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r, p->scal, slot_eta, slot_r,
+      delta, Hd, eta, Heta, r, p->partials);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }

@@ -54,7 +54,14 @@ int launch_project_tangent(dcora_problem *p, const double *X, const double *V,
 // OUT = proj_X(HV - V*sym(Y^T EG)) with S = sym(Y^T EG) precomputed
 int launch_rhess_correct(dcora_problem *p, const double *X, const double *S,
                          const double *V, const double *HV, double *OUT,
-                         int mask_flag);
+                         int mask_flag, bool with_dot = false);
+int launch_gradient_fused(dcora_problem *p, const double *X, const double *XQ,
+                          const double *G, double *EG, double *gf, double *S,
+                          int mask_flag);
+int launch_tcg_begin(dcora_problem *p, const double *gf, double *r, double *eta, double *Heta,
+                     int mask_flag);
+int launch_tcg_update(dcora_problem *p, int slot_eta, int slot_r, const double *delta,
+                      const double *Hd, double *eta, double *Heta, double *r, int mask_flag);
 // S[pose] = sym(Y^T EG) (d*d per pose block, 1 per sphere column): stored
 // column-aligned in a vector of the same shape (first d*d / 1 entries used)
 int launch_sym_ytg(dcora_problem *p, const double *X, const double *EG, double *S,

@@ -275,10 +275,11 @@ static int zero_counter(dcora_problem *p, int which) {
 }
 
 // Riemannian Hessian-vector product at x1: out = proj(V*Q - V*sym(Y^T EG))
+// with_dot: also leaves <v, out> in partial slot 0
 static int rhess(dcora_problem *p, const double *x1, const double *S, const double *v,
-                 double *tmp, double *out, int mask) {
+                 double *tmp, double *out, int mask, bool with_dot = false) {
   DCORA_TRY(launch_spmm(p, v, nullptr, tmp, mask));
-  return launch_rhess_correct(p, x1, S, v, tmp, out, mask);
+  return launch_rhess_correct(p, x1, S, v, tmp, out, mask, with_dot);
 }
 
 // EG, gf, S at x1 for the agents selected by `mask`; leaves <gf,gf> in partial 0.
@@ -287,13 +288,9 @@ static int rhess(dcora_problem *p, const double *x1, const double *S, const doub
 // SpMM epilogue, without a second pass over Q.
 static int gradient_at(dcora_problem *p, const double *x1, double *EG, double *gf,
                        double *S, int mask, const double *XQ = nullptr) {
-  if (XQ == nullptr) {
-    DCORA_TRY(launch_spmm(p, x1, p->has_G ? p->G : nullptr, EG, mask));
-  } else if (p->has_G) {
-    DCORA_TRY(launch_axpby(p, EG, -1, 1.0, XQ, -1, 1.0, p->G, mask));
-  } else {
-    DCORA_TRY(launch_copy(p, EG, XQ, mask));
-  }
+  if (XQ != nullptr)  // one fused pass: EG, gf, S and <gf, gf>
+    return launch_gradient_fused(p, x1, XQ, p->has_G ? p->G : nullptr, EG, gf, S, mask);
+  DCORA_TRY(launch_spmm(p, x1, p->has_G ? p->G : nullptr, EG, mask));
   DCORA_TRY(launch_project_tangent(p, x1, EG, gf, mask));
   DCORA_TRY(launch_sym_ytg(p, x1, EG, S, mask));
   const double *xs[1] = {gf};
@@ -459,11 +456,10 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
 
   for (int it = 0; it < max_outer && n_outer > 0; ++it) {
     // ---- tCG (SolversTR::tCG_TR), eta0 = 0
-    DCORA_TRY(launch_copy(p, r, gf, F_OUTER));
-    DCORA_TRY(launch_axpby(p, eta, -1, 0.0, gf, -1, 0.0, nullptr, F_OUTER));
-    // H eta is accumulated with eta (H eta += c H delta, the Hessian is linear on the
-    // tangent space), which saves the SpMM of a separate H*eta for the model decrease
-    DCORA_TRY(launch_axpby(p, Heta, -1, 0.0, gf, -1, 0.0, nullptr, F_OUTER));
+    // r = gf, eta = 0, Heta = 0.  H eta is accumulated with eta (H eta += c H delta, the
+    // Hessian is linear on the tangent space), which saves the SpMM of a separate H*eta
+    // for the model decrease
+    DCORA_TRY(launch_tcg_begin(p, gf, r, eta, Heta, F_OUTER));
     DCORA_TRY(launch_precond(p, x1, r, z, F_OUTER));
     {
       const double *xs[1] = {z}, *ys[1] = {r};
@@ -476,20 +472,11 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     pt.mark(1);
     ++n_outer_done;
     for (int j = 0; j < prm->RTR_tCG_iterations && n_tcg > 0; ++j) {
-      DCORA_TRY(rhess(p, x1, S, delta, t0, Hd, F_TCG));
-      {
-        const double *xs[1] = {delta}, *ys[1] = {Hd};
-        DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
-      }
+      DCORA_TRY(rhess(p, x1, S, delta, t0, Hd, F_TCG, true));  // + <delta, H delta>
       tcg_stepA_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
-      DCORA_TRY(launch_axpby(p, eta, -1, 1.0, eta, S_CETA, 1.0, delta, F_STEP));
-      DCORA_TRY(launch_axpby(p, Heta, -1, 1.0, Heta, S_CETA, 1.0, Hd, F_STEP));
-      DCORA_TRY(launch_axpby(p, r, -1, 1.0, r, S_CR, 1.0, Hd, F_STEP));
-      {
-        const double *xs[1] = {r};
-        DCORA_TRY(launch_dots(p, 1, xs, xs, F_STEP));
-      }
+      // eta += c delta, Heta += c Hd, r += c_r Hd and <r, r> in one pass
+      DCORA_TRY(launch_tcg_update(p, S_CETA, S_CR, delta, Hd, eta, Heta, r, F_STEP));
       DCORA_TRY(zero_counter(p, 1));
       tcg_stepB_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
                                                  p->scal, j, 0, prm->RTR_tCG_iterations,

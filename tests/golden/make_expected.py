@@ -24,24 +24,38 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import certify, manifold as mf, solver  # noqa: E402
 from tests.common import central_problem  # noqa: E402
 
-CASES = {  # name: (rank, seed, gradnorm tol, eta)
+CASES = {  # name: (rank, seed, gradnorm tol, eta[, init])
     "smallGrid3D": (5, 1, 1e-6, 1e-3),
-    "kitti_00": (5, 1, 1e-5, 1e-3),
     "sphere2500": (5, 1, 1e-5, 1e-3),
     "torus3D": (5, 1, 1e-5, 1e-3),
     "city10000": (5, 1, 1e-4, 1e-3),
-    "tiers": (4, 1, 1e-4, 1e-4),
+    # tiers (range-aided, configs[1]) is NOT recorded here: with the reference's tiny RA
+    # regularisation lambda_max/(1e6-1) the CPU oracle does not reach gradnorm 1e-4 within
+    # 2000 RTR iterations (13 min) even from the lifted ground truth; its parity is checked
+    # per operation (tests/test_gpu_problem.py) and on a default-parameter optimize call
+    # (tests/test_gpu_datasets.py::test_tiers_default_call_follows_the_oracle).
 }
+
+
+def start_point(P, info, seed, init):
+    """Seeded random feasible point, or the data file's ground truth lifted with [I; 0]
+    (kitti_00 has no VERTEX lines: falls back to random)."""
+    if init == "gt" and info["has_gt"]:
+        X = np.zeros((P.L.r, P.L.k))
+        X[:info["d"], :] = info["X_gt"]
+        return mf.project_manifold(P.L, X)
+    return mf.random_point(P.L, np.random.default_rng(seed))
 
 
 def main():
     path = os.path.join(HERE, "expected.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     for name in (sys.argv[1:] or CASES):
-        r, seed, tol, eta = CASES[name]
+        r, seed, tol, eta = CASES[name][:4]
+        init = CASES[name][4] if len(CASES[name]) > 4 else "random"
         t0 = time.time()
         P, g, info = central_problem(name, r)
-        X0 = mf.random_point(P.L, np.random.default_rng(seed))
+        X0 = start_point(P, info, seed, init)
         opt = solver.QuadraticOptimizer(P, solver.ROptParameters(
             RTR_iterations=2000, RTR_tCG_iterations=500, gradnorm_tol=tol))
         X = opt.optimize(X0)
@@ -49,7 +63,7 @@ def main():
         S = certify.certificate_matrix(P.L, X, P.Q)
         lam = float(certify.lambda_min(S))
         psd = bool(certify.fast_verification(S, eta)[0])
-        out[name] = dict(r=r, seed=seed, gradnorm_tol=tol, eta=eta, fInit=res.fInit, fOpt=res.fOpt,
+        out[name] = dict(r=r, seed=seed, init=init, gradnorm_tol=tol, eta=eta, fInit=res.fInit, fOpt=res.fOpt,
                          cost_2f=2 * res.fOpt, gradNormOpt=res.gradNormOpt,
                          outer_iters=res.outer_iters, inner_iters=res.inner_iters,
                          lambda_min=lam, is_psd=psd, oracle_seconds=time.time() - t0)

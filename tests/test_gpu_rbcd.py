@@ -42,7 +42,7 @@ def _random_X(blocks, r, K, seed):
 
 
 @pytest.mark.parametrize("name,robots", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 2),
-                                         ("range_aided_slam_test_2d", 2)])
+                                         ("range_aided_slam_test_2d", 2), ("kitti_00", 64)])
 def test_linear_term_and_cost_terms(name, robots):
     import dcora_b200 as dc
     from dcora_b200 import rbcd
@@ -65,8 +65,11 @@ def test_linear_term_and_cost_terms(name, robots):
     assert np.array_equal(solver_gpu.P.pack_columns(X, idx), X[:, idx])
 
 
+# kitti_00 / 64 agents is BASELINE.json configs[3] (70 poses per agent, the last takes the
+# remainder: the partition rule of examples/MultiRobotExample.cpp:56-118)
 @pytest.mark.parametrize("name,robots,acc", [("smallGrid3D", 5, False),
-                                             ("range_aided_slam_test_3d", 2, False)])
+                                             ("range_aided_slam_test_3d", 2, False),
+                                             ("kitti_00", 64, False)])
 def test_sweeps_follow_the_oracle(name, robots, acc):
     import dcora_b200 as dc
     from dcora_b200 import rbcd
