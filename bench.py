@@ -242,19 +242,25 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         p = S.plan
-        xh = torch.from_numpy(np.ascontiguousarray(S.get_X().T)).pin_memory()
-        out_h = torch.empty_like(xh).pin_memory()
+        # two pinned host buffers: the iterate goes host -> device at the start of every step
+        # and device -> host at its end; the buffers swap roles between steps (the host
+        # side of a caller keeps the result where the library wrote it)
+        hbuf = [torch.from_numpy(np.ascontiguousarray(S.get_X().T)).pin_memory(), None]
+        hbuf[1] = torch.empty_like(hbuf[0]).pin_memory()
         res_h = torch.zeros(2, dtype=torch.float64).pin_memory()
+        xdev = torch.empty_like(S.X)
+        xh = hbuf[0]
 
         def e2e_step():
-            S.X = xh.to(S.device, non_blocking=True)
+            xdev.copy_(hbuf[0], non_blocking=True)      # H2D of this step's input
+            S.X = xdev
             torch.cuda.current_stream().synchronize()
             S.iterate()
             f, g = S.monitor()
-            out_h.copy_(S.X, non_blocking=True)
+            hbuf[1].copy_(S.X, non_blocking=True)       # D2H of this step's result
             res_h[0], res_h[1] = f, g
             torch.cuda.current_stream().synchronize()
-            xh.copy_(out_h)
+            hbuf[0], hbuf[1] = hbuf[1], hbuf[0]
         for _ in range(min(1, args.warmup)):
             e2e_step()
         barrier()
@@ -372,6 +378,13 @@ def _cpu_agent_update(args_tuple):
     (rowptr, col, val, Ga, Xa, r, d, n, l, b, ra, reg) = args_tuple
     import scipy.sparse as sp
     from oracle import manifold as mf, solver
+    try:
+        # one BLAS thread per worker: the pool already uses every core (a forked worker
+        # inherits the parent's multi-threaded BLAS pool and would oversubscribe 8x)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     L = mf.Layout(r, d, n, l, b, ra=ra)
     Q = sp.csr_matrix((val, col, rowptr), shape=(L.k, L.k))
     P = solver.QuadraticProblem(L, Q, G=Ga, precond_reg=reg)

@@ -69,10 +69,13 @@ def build_examples(verbose=False):
     os.makedirs(EXAMPLE_BIN, exist_ok=True)
     out = []
     inc = os.path.join(HERE, "..", "include")
-    for name in sorted(os.listdir(EXAMPLES)):
-        if not name.endswith(".cpp"):
-            continue
-        src = os.path.join(EXAMPLES, name)
+    cpp_tests = os.path.join(HERE, "..", "tests", "cpp")
+    sources = [os.path.join(EXAMPLES, f) for f in sorted(os.listdir(EXAMPLES)) if f.endswith(".cpp")]
+    if os.path.isdir(cpp_tests):
+        sources += [os.path.join(cpp_tests, f) for f in sorted(os.listdir(cpp_tests))
+                    if f.endswith(".cpp")]
+    for src in sources:
+        name = os.path.basename(src)
         exe = os.path.join(EXAMPLE_BIN, name[:-4])
         deps = [src, os.path.join(inc, "dcora_b200.h"), os.path.join(inc, "dcora_b200", "DCORA.hpp")]
         if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):

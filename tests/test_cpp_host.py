@@ -66,3 +66,13 @@ def test_cpp_staircase_reaches_the_certified_optimum(exe, tmp_path, name):
     assert s["summary"] and s["certified"] == e["is_psd"]
     assert abs(s["cost_2f"] - e["cost_2f"]) <= 1e-8 * abs(e["cost_2f"])
     assert s["lambda_min"] > -e["eta"]
+
+
+@pytest.mark.gpu
+def test_cpp_manifold_and_problem_api(exe):
+    # tests/cpp/test_manifold_api.cpp: the reference's testManifold-style closed-form checks
+    # written against the C++ mirror, run on the device
+    binary = os.path.join(os.path.dirname(exe), "test_manifold_api")
+    out = subprocess.run([binary], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all checks passed" in out.stdout and "FAILED" not in out.stdout
