@@ -169,3 +169,59 @@ def test_staircase_driver_escapes_the_saddle_and_certifies():
     assert res.levels[0]["r"] == 3
     if len(res.levels) > 1:
         assert not res.levels[0]["is_psd"] and res.levels[-1]["f"] < res.levels[0]["f"]
+
+
+@pytest.mark.parametrize("name,r", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 5)])
+@pytest.mark.parametrize("precond", [True, False])
+def test_rgd_step_matches_oracle(name, r, precond):
+    # ROptMethod::RGD: one Riemannian gradient step with constant step size
+    # (QuadraticOptimizer.cpp:124-201), with and without the preconditioner
+    import dcora_b200 as dc
+    P, g, info = central_problem(name, r)
+    gp = gpu_problem(P)
+    P.reg = gp.precond_reg(0)
+    P._lu = None
+    X0 = mf.random_point(P.L, np.random.default_rng(3))
+    kw = dict(method="RGD", RGD_stepsize=1e-4, RGD_use_preconditioner=precond)
+    oo = solver.QuadraticOptimizer(P, solver.ROptParameters(**kw))
+    Xo = oo.optimize(X0)
+    go = dc.QuadraticOptimizer(gp, _params(**kw))
+    Xg = go.optimize(X0)
+    rg = go.getOptResult()
+    assert rel_err(Xg, Xo) < 1e-10
+    assert abs(rg.fInit - oo.result.fInit) <= 1e-12 * abs(oo.result.fInit)
+    assert abs(rg.fOpt - oo.result.fOpt) <= 1e-10 * abs(oo.result.fOpt)
+    assert abs(rg.gradNormOpt - oo.result.gradNormOpt) <= 1e-8 * oo.result.gradNormOpt
+
+
+def test_single_iteration_mode_shrinks_the_radius_until_accepted():
+    # RTR_iterations == 1: QuadraticOptimizer.cpp:254-273 re-runs the solver with the
+    # radius divided by 4 (at most 10 times) until the step is accepted
+    import dcora_b200 as dc
+    P, g, info = central_problem("smallGrid3D", 5)
+    gp = gpu_problem(P)
+    X0 = mf.random_point(P.L, np.random.default_rng(4))
+    kw = dict(RTR_iterations=1, RTR_tCG_iterations=50, RTR_initial_radius=1e4)
+    oo = solver.QuadraticOptimizer(P, solver.ROptParameters(**kw))
+    Xo = oo.optimize(X0)
+    go = dc.QuadraticOptimizer(gp, _params(**kw))
+    Xg = go.optimize(X0)
+    rg = go.getOptResult()
+    assert rg.fOpt < rg.fInit
+    assert abs(rg.fOpt - oo.result.fOpt) <= 1e-8 * abs(oo.result.fOpt)
+    assert rel_err(Xg, Xo) < 1e-6
+
+
+def test_polar_retraction_in_the_solver():
+    # the retraction variant is selectable (ROPTLIB's Stiefel default is qf; the
+    # reference's metric projections are polar): both must agree with the oracle
+    import dcora_b200 as dc
+    P, g, info = central_problem("smallGrid3D", 5)
+    gp = gpu_problem(P)
+    X0 = mf.random_point(P.L, np.random.default_rng(5))
+    oo = solver.QuadraticOptimizer(P, solver.ROptParameters(retraction="polar"))
+    Xo = oo.optimize(X0)
+    go = dc.QuadraticOptimizer(gp, _params(retraction=dc.RETRACT_POLAR))
+    Xg = go.optimize(X0)
+    assert rel_err(Xg, Xo) < 1e-7
+    assert abs(go.getOptResult().fOpt - oo.result.fOpt) <= 1e-9 * abs(oo.result.fOpt)
