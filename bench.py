@@ -253,7 +253,7 @@ def run_ours(args):
 
         def e2e_step():
             xdev.copy_(hbuf[0], non_blocking=True)      # H2D of this step's input
-            S.X = xdev
+            S.set_device_X(xdev)
             torch.cuda.current_stream().synchronize()
             S.iterate()
             f, g = S.monitor()

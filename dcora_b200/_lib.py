@@ -87,6 +87,7 @@ SYMBOLS = {
     "dcora_problem_halo_dim": (C.c_int64, [VP]),
     "dcora_problem_update_G": (C.c_int, [VP, VP, VP, c_uint8_p]),
     "dcora_problem_pack_columns": (C.c_int, [VP, VP, c_int32_p, C.c_int64, VP]),
+    "dcora_problem_set_iterate_tracking": (C.c_int, [VP, C.c_int32]),
     "dcora_problem_cost_terms": (C.c_int, [VP, VP, c_double_p, c_double_p]),
     "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
                                                 c_uint8_p, VP]),

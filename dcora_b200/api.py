@@ -337,6 +337,11 @@ class QuadraticProblem:
             self.h, a.ptr, idx.ctypes.data_as(_lib.c_int32_p), len(idx), o.ptr))
         return out
 
+    def set_iterate_tracking(self, on=True):
+        """See dcora_problem_set_iterate_tracking: call again after writing to the tracked
+        device buffer yourself."""
+        check(self.lib.dcora_problem_set_iterate_tracking(self.h, int(bool(on))))
+
     def cost_terms(self, X):
         a = _Arg(X, self.r, self.K)
         q = (C.c_double * self.A)()

@@ -191,6 +191,10 @@ struct dcora_problem {
   std::shared_ptr<dcora::DeviceMatrices> M;
   std::shared_ptr<dcora::DeviceCoupling> C;  // cross-agent coupling (RBCD), optional
   double *xe = nullptr;            // [X | H] extended vector, r*(K+KH)
+  // iterate tracking (dcora_problem_set_iterate_tracking): `tracked` is the
+  // caller's device buffer whose content equals the first K columns of xe
+  bool tracking = false;
+  const double *tracked = nullptr;
   double *hstage = nullptr;        // halo staging (reference layout)
   // launch lists of the caller's current agent subset (null: whole batch)
   std::shared_ptr<dcora::ActiveSet> act;

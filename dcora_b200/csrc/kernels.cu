@@ -11,6 +11,7 @@
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
+#include "solver.cuh"
 
 namespace dcora {
 
@@ -639,6 +640,22 @@ permute_kernel(int64_t K, int R, const int *__restrict__ perm,
   else out[rc * R + q] = in[c * R + q];
 }
 
+// internal -> reference write-back of the columns of the listed chunks only
+__global__ void __launch_bounds__(128)
+export_chunks_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
+                     int mask_flag, const int *__restrict__ list, int R,
+                     const int *__restrict__ perm, const double *__restrict__ in,
+                     double *__restrict__ out) {
+  const Chunk ch = chunks[list ? list[blockIdx.x] : blockIdx.x];
+  if (!agent_on(flags, ch.agent, mask_flag)) return;
+  const int len = ch.ncols * R;
+  for (int i = threadIdx.x; i < len; i += 128) {
+    const int c = ch.col0 + i / R, q = i - (i / R) * R;
+    const size_t rc = perm ? (size_t)perm[c] : (size_t)c;
+    out[rc * R + q] = in[(size_t)c * R + q];
+  }
+}
+
 // scal[a*NS + dst[s]] = sum over agent a's chunks of partial slot s
 struct ReduceArgs { int n; int dst[NPART]; };
 __global__ void __launch_bounds__(128)
@@ -813,6 +830,17 @@ int launch_permute_cols(dcora_problem *p, const int *perm, int64_t ncols,
   const int grid = (int)((tot + 255) / 256);
   permute_kernel<<<grid, 256, 0, p->stream>>>(ncols, r, perm, in, out,
                                               to_internal ? 1 : 0);
+  DCORA_LAUNCH_CHECK(p);
+  return DCORA_OK;
+}
+
+int export_active_columns(dcora_problem *p, const double *src, double *dst, int mask_flag) {
+  DeviceMatrices &M = *p->M;
+  const ActiveSet *as = active_set(p, mask_flag);
+  if (as && as->n_chunks == 0) return DCORA_OK;
+  export_chunks_kernel<<<as ? as->n_chunks : M.nchunks, 128, 0, p->stream>>>(
+      M.chunks, p->flags, mask_flag, as ? as->chunks : nullptr, p->r,
+      M.identity_perm ? nullptr : M.perm, src, dst);
   DCORA_LAUNCH_CHECK(p);
   return DCORA_OK;
 }

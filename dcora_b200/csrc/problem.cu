@@ -69,6 +69,9 @@ int import_matrix(dcora_problem *p, const double *src, double *dst, int r) {
 
 int export_matrix(dcora_problem *p, const double *src, double *dst, int r) {
   DeviceMatrices &M = *p->M;
+  // any write into the tracked buffer other than the solver's own write-back
+  // (which re-establishes it afterwards) ends the equality with p->xe
+  if (dst == p->tracked) p->tracked = nullptr;
   const size_t bytes = (size_t)M.K * r * sizeof(double);
   const bool dev = is_device_ptr(dst);
   if (M.identity_perm) {
@@ -85,6 +88,23 @@ int export_matrix(dcora_problem *p, const double *src, double *dst, int r) {
   // The C-ABI is synchronous: results are complete when a call returns, also
   // for device destinations (the caller's stream is not ours).
   DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+bool pointer_on_device(const void *ptr) { return is_device_ptr(ptr); }
+
+int acquire_iterate(dcora_problem *p, const double *X, double *buf, double **out) {
+  if (p->tracking && p->xe && is_device_ptr(X)) {
+    if (X != p->tracked) {
+      DCORA_TRY(import_matrix(p, X, p->xe, p->r));
+      p->tracked = X;
+    }
+    *out = p->xe;
+    return DCORA_OK;
+  }
+  if (!buf) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, buf, p->r));
+  *out = buf;
   return DCORA_OK;
 }
 
@@ -421,11 +441,23 @@ int dcora_problem_rgrad(dcora_problem *p, const double *X, double *RG) {
   return export_matrix(p, o, RG, p->r);
 }
 
+int dcora_problem_set_iterate_tracking(dcora_problem *p, int32_t on) {
+  if (!p) return DCORA_ERR_ARG;
+  if (on && !p->C) {
+    set_error("dcora_problem_set_iterate_tracking: register the coupling first "
+              "(dcora_problem_set_coupling)");
+    return DCORA_ERR_ARG;
+  }
+  p->tracking = on != 0;
+  p->tracked = nullptr;
+  return DCORA_OK;
+}
+
 int dcora_problem_rgradnorm(dcora_problem *p, const double *X, double *norm_out) {
   DCORA_ENTER(p);
-  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
-  if (!x || !t || !o) return DCORA_ERR_ALLOC;
-  DCORA_TRY(import_matrix(p, X, x, p->r));
+  double *x = nullptr, *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
+  if (!t || !o) return DCORA_ERR_ALLOC;
+  DCORA_TRY(acquire_iterate(p, X, p->vec(WS_IO0), &x));
   DCORA_TRY(launch_spmm(p, x, p->has_G ? p->G : nullptr, t, -1));
   DCORA_TRY(launch_project_tangent(p, x, t, o, -1));
   const double *xs[1] = {o};

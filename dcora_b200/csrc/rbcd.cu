@@ -99,7 +99,7 @@ int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
   DCORA_CUDA(upload(&C->rem_assign, H.rem_assign));
   DCORA_CUDA(upload(&C->rem_val, H.rem_val));
   p->C = C;
-  cudaFree(p->xe); p->xe = nullptr;
+  cudaFree(p->xe); p->xe = nullptr; p->tracked = nullptr;
   cudaFree(p->hstage); p->hstage = nullptr;
   return DCORA_OK;
 }
@@ -121,8 +121,14 @@ int dcora_problem_update_G(dcora_problem *p, const double *X, const double *Hh,
     return DCORA_ERR_ARG;
   }
   const int r = p->r;
-  if (!p->xe) DCORA_CUDA(cudaMalloc(&p->xe, sizeof(double) * (size_t)std::max<int64_t>(1, (M.K + C.KH) * r)));
-  DCORA_TRY(import_matrix(p, X, p->xe, r));
+  if (!p->xe) {
+    DCORA_CUDA(cudaMalloc(&p->xe, sizeof(double) * (size_t)std::max<int64_t>(1, (M.K + C.KH) * r)));
+    p->tracked = nullptr;
+  }
+  {
+    double *xin = nullptr;  // tracked: no conversion when X is the tracked buffer
+    DCORA_TRY(acquire_iterate(p, X, p->xe, &xin));
+  }
   if (C.KH > 0) {
     double *dst = p->xe + (size_t)M.K * r;
     const size_t bytes = sizeof(double) * (size_t)C.KH * r;
@@ -207,9 +213,9 @@ int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out
                              double *lin_out) {
   if (!p || !X) return DCORA_ERR_ARG;
   DCORA_CUDA(cudaSetDevice(p->M->device));
-  double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1);
-  if (!x || !t) return DCORA_ERR_ALLOC;
-  DCORA_TRY(import_matrix(p, X, x, p->r));
+  double *x = nullptr, *t = p->vec(WS_IO1);
+  if (!t) return DCORA_ERR_ALLOC;
+  DCORA_TRY(acquire_iterate(p, X, p->vec(WS_IO0), &x));
   DCORA_TRY(launch_spmm(p, x, nullptr, t, -1));
   const double *xs[2] = {t, x};
   const double *ys[2] = {x, p->G};

@@ -567,9 +567,27 @@ extern "C" int dcora_rtr_solve(dcora_problem *p, const double *X0, double *Xopt,
   DCORA_CUDA(cudaSetDevice(p->M->device));
   dcora_ropt_params prm;
   if (params) prm = *params; else dcora_ropt_params_default(&prm);
-  double *x1 = p->vec(WS_X1);
-  if (!x1) return DCORA_ERR_ALLOC;
-  DCORA_TRY(import_matrix(p, X0, x1, p->r));
-  DCORA_TRY(rtr_solve_device(p, x1, &prm, active, results));
-  return export_matrix(p, x1, Xopt, p->r);
+  double *x1 = nullptr;
+  const bool track = p->tracking && p->xe && pointer_on_device(X0) && pointer_on_device(Xopt);
+  // in place on the tracked buffer: only the updated agents' columns change
+  const bool in_place_tracked = track && X0 == Xopt && X0 == p->tracked;
+  if (track) {
+    DCORA_TRY(acquire_iterate(p, X0, nullptr, &x1));   // the iterate lives in p->xe
+  } else {
+    x1 = p->vec(WS_X1);
+    if (!x1) return DCORA_ERR_ALLOC;
+    DCORA_TRY(import_matrix(p, X0, x1, p->r));
+  }
+  const int rc_solve = rtr_solve_device(p, x1, &prm, active, results);
+  if (track) p->tracked = nullptr;   // xe changed; re-established by the write-back below
+  if (rc_solve < 0) return rc_solve;
+  if (in_place_tracked) {
+    DCORA_TRY(export_active_columns(p, x1, Xopt, F_USER));
+    DCORA_CUDA(cudaStreamSynchronize(p->stream));
+    p->tracked = Xopt;
+    return DCORA_OK;
+  }
+  const int rc_exp = export_matrix(p, x1, Xopt, p->r);
+  if (rc_exp >= 0 && track) p->tracked = Xopt;
+  return rc_exp;
 }

@@ -8,6 +8,13 @@ namespace dcora {
 int import_matrix(dcora_problem *p, const double *src, double *dst, int r);
 int export_matrix(dcora_problem *p, const double *src, double *dst, int r);
 int read_scalars(dcora_problem *p);
+bool pointer_on_device(const void *ptr);
+// Internal-layout view of the caller's iterate X (r x K): the tracked copy in
+// p->xe when X is the tracked device buffer, else X imported into `buf` (or into
+// p->xe, which then becomes the tracked copy, when tracking is on).
+int acquire_iterate(dcora_problem *p, const double *X, double *buf, double **out);
+// Reference-layout write-back of the active agents' columns only
+int export_active_columns(dcora_problem *p, const double *src, double *dst, int mask_flag);
 
 // scal[slot] = 0.5*partial0 (+ partial1 if with_G) per agent
 int launch_combine_f(dcora_problem *p, int slot, int with_G, int mask_flag);

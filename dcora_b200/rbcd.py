@@ -175,6 +175,8 @@ class RBCD:
         self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
         segs = [plan.seg] * world if world > 1 else []
         self.P.set_coupling(plan.coupling, segs)
+        # the iterate lives in ONE device buffer (self.X) that only the library writes
+        self.P.set_iterate_tracking(True)
         self.params = params or ROptParameters()
         self.opt = QuadraticOptimizer(self.P, self.params)
         self.device = torch.device("cuda", device)
@@ -192,7 +194,12 @@ class RBCD:
         t = self.torch
         p = self.plan
         Xl = np.ascontiguousarray(X_global[:, p.c0:p.c0 + p.K].T)
-        self.X = t.from_numpy(Xl).to(self.device)
+        self.set_device_X(t.from_numpy(Xl).to(self.device))
+
+    def set_device_X(self, X_dev):
+        """Replace the iterate by a device tensor (K_local, r) written by the caller."""
+        self.X = X_dev
+        self.P.set_iterate_tracking(True)      # forget the tracked copy
 
     def get_X(self):
         """numpy (r, K_local)."""

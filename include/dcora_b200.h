@@ -243,6 +243,17 @@ int dcora_problem_update_G(dcora_problem *p, const double *X, const double *H,
 int dcora_problem_pack_columns(dcora_problem *p, const double *X,
                                const int32_t *idx, int64_t count, double *out);
 
+/* Iterate tracking for drivers that keep ONE device-resident iterate buffer and
+ * change it only through this library (the RBCD loop: Agent::X,
+ * include/DCORA/Agent.h:698).  While tracking is on, the handle remembers the
+ * device pointer whose content equals its internal copy of the iterate: calls
+ * that receive that same pointer (update_G, rtr_solve, cost_terms, rgradnorm)
+ * skip the layout conversion of their input, and an in-place rtr_solve writes
+ * back only the columns of the agents it updated.  The caller must call this
+ * function again (on = 1 re-arms, forgetting the pointer) whenever it has
+ * written to the buffer itself.  Needs a registered coupling; off by default. */
+int dcora_problem_set_iterate_tracking(dcora_problem *p, int32_t on);
+
 /* Per-agent 0.5 <X Q, X> and <X, G>: the global cost of the partitioned
  * problem is sum_a quad_a + 0.5 lin_a (cross terms appear in two agents). */
 int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,

@@ -114,3 +114,38 @@ def test_rbcd_converges_to_the_certified_optimum():
                 break
     assert gn < 1e-4
     assert abs(2 * f - 1025.3980521) < 1e-5
+
+
+@pytest.mark.parametrize("name,robots", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 2)])
+def test_iterate_tracking_does_not_change_results(name, robots):
+    # dcora_problem_set_iterate_tracking only skips layout conversions of the unchanged
+    # device buffer and writes back the updated agents' columns: bit-identical iterates
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup(name, robots, r)
+    X0 = _random_X(blocks, r, gp.K, 2)
+    out = []
+    for tracking in (True, False):
+        G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0))
+        G.set_X(X0)
+        G.P.set_iterate_tracking(tracking)
+        hist = []
+        for it in range(3):
+            G.iterate()
+            hist.append(G.monitor())
+        out.append((G.get_X(), hist))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+    # a caller that overwrites the tracked buffer re-arms the tracking
+    G.P.set_iterate_tracking(True)
+    G.iterate()
+    Xa = G.get_X()
+    G.X.copy_(G.torch.from_numpy(np.ascontiguousarray(X0.T)).to(G.device))
+    G.set_device_X(G.X)
+    G.iterate()
+    H2 = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0))
+    H2.set_X(X0)
+    H2.iterate()
+    assert np.array_equal(G.get_X(), H2.get_X())
+    assert not np.array_equal(G.get_X(), Xa)
