@@ -140,7 +140,7 @@ struct DeviceFactor {
   int max_levels = 0;
   unsigned long long *tape = nullptr;  // all tapes, 8-byte words
   long long *tape_off = nullptr;       // A * nwarps: first word of each warp's tape
-  int *tape_chunks = nullptr;          // A * nwarps: length in 1 KB chunks
+  int *tape_chunks = nullptr;          // A * nwarps: length in TAPE_CHUNK_WORDS chunks
   int *nlev = nullptr;                 // A * 2: levels forward / backward
   void release();
 };

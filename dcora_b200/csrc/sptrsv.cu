@@ -35,8 +35,10 @@ namespace {
 
 constexpr int TRSV_THREADS = 256;
 constexpr int TRSV_NW = TRSV_THREADS / 32;      // warps per CTA
-constexpr int CHW = TAPE_CHUNK_WORDS;           // words per chunk (1 KB)
-constexpr int NCH = 8;                          // chunks per ring (8 KB per warp)
+constexpr int CHW = TAPE_CHUNK_WORDS;           // words per chunk (2 KB)
+constexpr int NCH = 4;                          // chunks per ring (8 KB per warp): a phase-A
+                                                // iteration is ~1 KB, so 2 KB chunks halve the
+                                                // ring bookkeeping (arm + bulk copy) per iteration
 constexpr int RING_WORDS = NCH * CHW;
 constexpr int TRSV_SMEM = TRSV_NW * (RING_WORDS * 8 + NCH * 8);
 

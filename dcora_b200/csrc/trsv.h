@@ -31,7 +31,7 @@ namespace dcora {
 
 constexpr int TRSV_SMALL_BLOCK = 32;  // diagonal blocks of <= 32 rows: one warp, lane = row
 constexpr int TRSV_MAX_BLOCK = 512;   // larger ND blocks are split into a chain
-constexpr int TAPE_CHUNK_WORDS = 128; // 1 KB bulk-copy granularity of the tape ring
+constexpr int TAPE_CHUNK_WORDS = 256; // 2 KB bulk-copy granularity of the tape ring
 
 struct AgentTape {
   int k = 0, nblocks = 0, nwarps = 0, dh = 0;
