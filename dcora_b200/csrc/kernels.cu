@@ -316,9 +316,10 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
                 const double *__restrict__ V, const double *__restrict__ HV,
                 const double *S, double *__restrict__ OUT,
                 double *__restrict__ AUX, double *__restrict__ partials) {
-  // `partials` (optional, OP_RHESS / OP_GRAD): the chunk's share of <V, OUT>
-  // (OP_RHESS: <delta, H delta>) or <OUT, OUT> (OP_GRAD: <gf, gf>) goes to
-  // partial slot 0 -- the fused form of a following dots_kernel launch.
+  // `partials` (optional, OP_RHESS / OP_GRAD / OP_PROJECT): the chunk's share of
+  // <V, OUT> (OP_RHESS: <delta, H delta>), <OUT, OUT> (OP_GRAD: <gf, gf>) or
+  // <OUT, AUX> (OP_PROJECT after K5: <z, r>) goes to partial slot 0 -- the fused
+  // form of a following dots_kernel launch.
   constexpr int D = DH - 1;
   constexpr int PPW = Map<DH>::PPW;
   __shared__ double red_sm[4];
@@ -354,7 +355,11 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
       if (a == D) {  // translation column: Euclidean factor
         if (OP == OP_PROJECT) {
 #pragma unroll
-          for (int q = 0; q < R; ++q) OUT[o + q] = V[o + q];
+          for (int q = 0; q < R; ++q) {
+            const double v = V[o + q];
+            OUT[o + q] = v;
+            if (partials != nullptr) dsum = fma(v, AUX[o + q], dsum);
+          }
         } else if (OP == OP_RHESS) {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
@@ -410,6 +415,10 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
         double Vb[D][R];
         load_block<R, D>(V + pb, Vb);
         stiefel_proj_col<R, D>(Yb, Vb, a, out);
+        if (partials != nullptr) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) dsum = fma(out[q], AUX[o + q], dsum);
+        }
       } else if (OP == OP_RHESS) {
         double Vb[D][R], Wb[D][R];
         load_block<R, D>(V + pb, Vb);
@@ -465,7 +474,7 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         double v;
-        if (OP == OP_PROJECT) v = V[o + q];
+        if (OP == OP_PROJECT) { v = V[o + q]; if (partials != nullptr) dsum = fma(v, AUX[o + q], dsum); }
         else if (OP == OP_RHESS) { v = HV[o + q]; dsum = fma(V[o + q], v, dsum); }
         else if (OP == OP_GRAD) {
           v = HV ? V[o + q] + HV[o + q] : V[o + q];
@@ -517,6 +526,7 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
         const double oq = fma(-t, y[q], w[q]);
         OUT[o + q] = oq;
         if (OP == OP_RHESS) dsum = fma(V[o + q], oq, dsum);
+        if (OP == OP_PROJECT && partials != nullptr) dsum = fma(oq, AUX[o + q], dsum);
       }
     } else {
       if (OP != OP_PROJ_MANIFOLD) {
@@ -529,7 +539,7 @@ manifold_kernel(const Chunk *__restrict__ chunks, const int *__restrict__ flags,
     }
   }
   }
-  if ((OP == OP_RHESS || OP == OP_GRAD) && partials != nullptr) {
+  if ((OP == OP_RHESS || OP == OP_GRAD || OP == OP_PROJECT) && partials != nullptr) {
     const double t = block_sum<128>(dsum, red_sm);
     if (threadIdx.x == 0) partials[(size_t)cid * NPART + 0] = t;
   }
@@ -738,8 +748,11 @@ static int launch_manifold(dcora_problem *p, const double *X, const double *V,
 }
 
 int launch_project_tangent(dcora_problem *p, const double *X, const double *V,
-                           double *OUT, int mask_flag) {
-  return launch_manifold<OP_PROJECT>(p, X, V, nullptr, nullptr, OUT, mask_flag);
+                           double *OUT, int mask_flag, const double *dot_with) {
+  // dot_with (optional): also leaves <OUT, dot_with> in partial slot 0
+  return launch_manifold<OP_PROJECT>(p, X, V, nullptr, nullptr, OUT, mask_flag,
+                                     const_cast<double *>(dot_with),
+                                     dot_with ? p->partials : nullptr);
 }
 int launch_rhess_correct(dcora_problem *p, const double *X, const double *S,
                          const double *V, const double *HV, double *OUT,

@@ -50,7 +50,7 @@ int launch_spmm(dcora_problem *p, const double *X, const double *G, double *Y,
                 int mask_flag);
 // Manifold ops (per chunk; mask as above)
 int launch_project_tangent(dcora_problem *p, const double *X, const double *V,
-                           double *OUT, int mask_flag);
+                           double *OUT, int mask_flag, const double *dot_with = nullptr);
 // OUT = proj_X(HV - V*sym(Y^T EG)) with S = sym(Y^T EG) precomputed
 int launch_rhess_correct(dcora_problem *p, const double *X, const double *S,
                          const double *V, const double *HV, double *OUT,
@@ -88,7 +88,8 @@ int launch_reduce_scalars(dcora_problem *p, int nslots, const int *dst_slots);
 
 // preconditioner application z = proj_X( (Q+reg I)^-1 v ) (sptrsv.cu)
 int launch_precond(dcora_problem *p, const double *X, const double *V, double *OUT,
-                   int mask_flag, unsigned long long *trace = nullptr, int trace_agent = 0);
+                   int mask_flag, unsigned long long *trace = nullptr, int trace_agent = 0,
+                   const double *dot_with = nullptr);
 struct AgentTape;
 int upload_factor(dcora::DeviceMatrices *M, const std::vector<HostFactor> &F,
                   std::vector<AgentTape> &tapes, int cluster, const HostLayout &H);

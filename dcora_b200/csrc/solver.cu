@@ -460,11 +460,7 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     // Hessian is linear on the tangent space), which saves the SpMM of a separate H*eta
     // for the model decrease
     DCORA_TRY(launch_tcg_begin(p, gf, r, eta, Heta, F_OUTER));
-    DCORA_TRY(launch_precond(p, x1, r, z, F_OUTER));
-    {
-      const double *xs[1] = {z}, *ys[1] = {r};
-      DCORA_TRY(launch_dots(p, 1, xs, ys, F_OUTER));
-    }
+    DCORA_TRY(launch_precond(p, x1, r, z, F_OUTER, nullptr, 0, r));  // + <z, r>
     tcg_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, -1, 0.0, nullptr, F_TCG));
@@ -484,17 +480,15 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       DCORA_LAUNCH_CHECK(p);
       pt.mark(2);
       ++n_inner_done;
-      DCORA_TRY(launch_precond(p, x1, r, z, F_TCG));
-      {
-        const double *xs[1] = {z}, *ys[1] = {r};
-        DCORA_TRY(launch_dots(p, 1, xs, ys, F_TCG));
-      }
+      DCORA_TRY(launch_precond(p, x1, r, z, F_TCG, nullptr, 0, r));  // + <z, r>
       tcg_stepC_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       // delta = -z + beta * delta
       DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, S_BETA, 1.0, delta, F_TCG));
-      DCORA_TRY(read_counters(p, cnt));
-      n_tcg = cnt[1];
+      if (j + 1 < prm->RTR_tCG_iterations) {   // else the loop ends anyway
+        DCORA_TRY(read_counters(p, cnt));
+        n_tcg = cnt[1];
+      }
       pt.mark(3);
     }
     // ---- candidate, model decrease, rho (SolversTR::Run)
@@ -514,8 +508,10 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     rtr_accept_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
                                                 max_outer, single_mode, counters);
     DCORA_LAUNCH_CHECK(p);
-    DCORA_TRY(read_counters(p, cnt));
-    n_outer = cnt[0];
+    if (it + 1 < max_outer) {   // else the loop ends anyway (read_scalars syncs below)
+      DCORA_TRY(read_counters(p, cnt));
+      n_outer = cnt[0];
+    }
     pt.mark(5);
     if (prm->time_bound_s > 0.0) {
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count();

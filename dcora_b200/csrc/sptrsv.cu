@@ -486,13 +486,14 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
 }
 
 int launch_precond(dcora_problem *p, const double *X, const double *V, double *OUT,
-                   int mask_flag, unsigned long long *trace, int trace_agent) {
+                   int mask_flag, unsigned long long *trace, int trace_agent,
+                   const double *dot_with) {
   DeviceMatrices &M = *p->M;
   const DeviceFactor &F = M.F;
   if (!F.present) {
     // Graph::hasPreconditioner() false: the reference only projects
     // (QuadraticProblem.cpp:78-83)
-    return launch_project_tangent(p, X, V, OUT, mask_flag);
+    return launch_project_tangent(p, X, V, OUT, mask_flag, dot_with);
   }
   double *panel = p->vec(WS_TRSV_PANEL);
   double *tmp = p->vec(WS_TRSV_TMP);
@@ -506,7 +507,7 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
       default: DCORA_TRY((launch_trsv<R, DH, 8>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
     }
   })
-  return launch_project_tangent(p, X, sol, OUT, mask_flag);
+  return launch_project_tangent(p, X, sol, OUT, mask_flag, dot_with);
 }
 
 }  // namespace dcora
