@@ -163,7 +163,7 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
       const int niter = lo32(rh), gpt = hi32(rh);
       const unsigned long long d0 = rd.word(pos + 1 + 2 * g), d1 = rd.word(pos + 2 + 2 * g);
       const int r0 = lo32(d0), nrows = hi32(d0), pbase = lo32(d1);
-      pos += 17;
+      pos = (pos + 17 + 3) & ~3;  // the iterations start 32-byte aligned on the tape
       // lane (g, a) owns COLUMN a of its group's block: it needs one row of the
       // source pose (R doubles of Y) per block and accumulates all DH rows of
       // the product; the 4 lanes of a group are summed once per round.
@@ -204,8 +204,17 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
           for (int s2 = 0; s2 + 1 < PFD; ++s2) yq[s2][q] = yq[s2 + 1][q];
         }
         if (a < DH) {
+          // lane (g, a) owns DH consecutive tape words: column a of its block
+          const int base = pos + 4 + (g * DH + a) * DH;
+          if constexpr (DH == 4) {
+            const double2 *mp =
+                reinterpret_cast<const double2 *>(rd.ring + (base & (RING_WORDS - 1)));
+            const double2 m01 = mp[0], m23 = mp[1];
+            m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
+          } else {
 #pragma unroll
-          for (int i = 0; i < DH; ++i) m[i] = rd.dword(pos + 4 + i * (8 * DH) + g * DH + a);
+            for (int i = 0; i < DH; ++i) m[i] = rd.dword(base + i);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < DH; ++i) m[i] = 0.0;

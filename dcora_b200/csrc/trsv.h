@@ -16,7 +16,9 @@
 //     n_rounds x round:
 //        {niter, gpt}
 //        8 x slot ( {row0 | -1, nrows}, {perm_base, 0} )   one slot per 4-lane group
-//        niter x ( 4 words: source rows c[0..7] ; DH x 8 x DH doubles: [a][group][b] )
+//        zero padding to a multiple of 4 words
+//        niter x ( 4 words: source rows c[0..7] ; 8 x DH x DH doubles: [group][b][a],
+//                  i.e. lane (group, b) owns DH consecutive words = column b of its block )
 //     B header   {n_small, n_large}
 //     n_small x  {row0, w} {direct, 0} ceil(w/2) words perm[] , w(w+1)/2 doubles
 //     n_large x  {src_row0, len} {dest_row, dest_perm} , len doubles

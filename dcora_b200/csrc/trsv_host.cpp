@@ -305,6 +305,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
               tp.push_back(pack2(0, 0));
             }
           }
+          while (tp.size() % 4) tp.push_back(0);  // iterations start 32-byte aligned
           for (int it = 0; it < rd.niter; ++it) {
             int c[8];
             const double *vp[8];
@@ -319,11 +320,12 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
               }
             }
             for (int g = 0; g < 8; g += 2) tp.push_back(pack2(c[g], c[g + 1]));
-            // block row a of all 8 groups together: the 32 lanes (group, column)
-            // of a warp read 32 consecutive words (no shared-memory bank conflict)
-            for (int a = 0; a < dh; ++a)
-              for (int g = 0; g < 8; ++g)
-                for (int bb = 0; bb < dh; ++bb)
+            // lane (group g, column bb) owns DH consecutive words: its column of the
+            // block, rows 0..DH-1 (one address computation and, for DH = 4, two
+            // 128-bit shared loads per iteration on the device)
+            for (int g = 0; g < 8; ++g)
+              for (int bb = 0; bb < dh; ++bb)
+                for (int a = 0; a < dh; ++a)
                   tp.push_back(dbits(vp[g] ? vp[g][a * dh + bb] : 0.0));
             out->stored_values += 8 * bs;
           }
@@ -395,13 +397,14 @@ void agent_tape_apply_host(const AgentTape &S, const double *b, double *x, doubl
             p += 2;
           }
           std::vector<double> acc(8 * 4, 0.0);
+          p = (p + 3) & ~(size_t)3;
           for (int it = 0; it < niter; ++it) {
             int c[8];
             for (int g = 0; g < 8; g += 2) { c[g] = lo32(tp[p]); c[g + 1] = hi32(tp[p]); ++p; }
             for (int g = 0; g < 8; ++g)
               for (int a = 0; a < dh; ++a)
                 for (int bb = 0; bb < dh; ++bb)
-                  acc[g * 4 + a] += bitsd(tp[p + (size_t)a * 8 * dh + g * dh + bb]) * Y[c[g] + bb];
+                  acc[g * 4 + a] += bitsd(tp[p + (size_t)(g * dh + bb) * dh + a]) * Y[c[g] + bb];
             p += 8 * bs;
           }
           for (int g = 0; g < 8; g += gpt) {
