@@ -218,6 +218,15 @@ struct RelativePosePoseMeasurement {  // include/DCORA/Measurements.h (pose-pose
   double kappa = 1, tau = 1, weight = 1;
 };
 
+// Range measurement between two translation variables (pose or landmark), as the
+// reference's RangeMeasurement (include/DCORA/Measurements.h): unit sphere k of
+// the lifted problem is r_k = (t_src - t_dst) / ||.|| (src/DCORA_utils.cpp:1136-1137).
+struct RangeMeasurement {
+  unsigned p1 = 0, p2 = 0;            // source / destination index
+  bool landmark1 = false, landmark2 = false;  // endpoint is a landmark (else a pose)
+  double range = 1, precision = 1, weight = 1;
+};
+
 namespace detail {
 // Quaternion -> rotation matrix WITHOUT normalising the quaternion: the
 // reference calls Eigen::Quaterniond(w,x,y,z).toRotationMatrix()
@@ -313,13 +322,45 @@ class Graph {
   void setMeasurements(const std::vector<RelativePosePoseMeasurement> &measurements) {
     DCORA_B200_CHECK(type_ == GraphType::PoseGraph, "pose-pose measurements only");
     meas_ = measurements;
-    n_ = 0;
+    ranges_.clear();
+    n_ = 0; l_ = 0; b_ = 0;
     for (const auto &m : meas_) {
       DCORA_B200_CHECK(m.d == d_, "measurement dimension mismatch");
       n_ = std::max(n_, std::max(m.p1, m.p2) + 1);
     }
     clearDataMatrices();
   }
+  // Range-aided graph: pose-pose edges + range edges (one unit sphere per range,
+  // in the order given); `num_landmarks` landmark positions.  Column ordering
+  // [Y1..Yn | r1..rl | p1..pn | L1..Lb] (LiftedVariable.h:148-152).
+  void setMeasurements(const std::vector<RelativePosePoseMeasurement> &measurements,
+                       const std::vector<RangeMeasurement> &ranges, unsigned num_landmarks = 0) {
+    DCORA_B200_CHECK(type_ == GraphType::RangeAidedSLAMGraph, "range-aided graph expected");
+    meas_ = measurements;
+    ranges_ = ranges;
+    n_ = 0;
+    for (const auto &m : meas_) {
+      DCORA_B200_CHECK(m.d == d_, "measurement dimension mismatch");
+      n_ = std::max(n_, std::max(m.p1, m.p2) + 1);
+    }
+    for (const auto &rg : ranges_) {
+      if (!rg.landmark1) n_ = std::max(n_, rg.p1 + 1); else num_landmarks = std::max(num_landmarks, rg.p1 + 1);
+      if (!rg.landmark2) n_ = std::max(n_, rg.p2 + 1); else num_landmarks = std::max(num_landmarks, rg.p2 + 1);
+    }
+    l_ = (unsigned)ranges_.size();
+    b_ = num_landmarks;
+    clearDataMatrices();
+  }
+  // column of the lifted variable holding rotation column c / the translation of pose i,
+  // unit sphere e, landmark j (SE: interleaved; RA: DCORA_utils.cpp:2156-2165)
+  unsigned rotationColumn(unsigned i, unsigned c) const {
+    return type_ == GraphType::PoseGraph ? i * (d_ + 1) + c : i * d_ + c;
+  }
+  unsigned translationColumn(unsigned i) const {
+    return type_ == GraphType::PoseGraph ? i * (d_ + 1) + d_ : d_ * n_ + l_ + i;
+  }
+  unsigned unitSphereColumn(unsigned e) const { return d_ * n_ + e; }
+  unsigned landmarkColumn(unsigned j) const { return d_ * n_ + l_ + n_ + j; }
   // Inject data matrices built elsewhere (e.g. by the reference's own Graph).
   void setQuadraticMatrix(unsigned n, unsigned l, unsigned b, SparseMatrix Q) {
     n_ = n; l_ = l; b_ = b;
@@ -359,12 +400,18 @@ class Graph {
  private:
   // Q = A^T Omega A with, per edge i -> j, T = [R t; 0 1] and
   // Omega = diag(w kappa, .., w tau):  Q_ii += T Omega T^T, Q_ij -= T Omega,
-  // Q_ji -= Omega T^T, Q_jj += Omega   (Graph.cpp:579-683).
+  // Q_ji -= Omega T^T, Q_jj += Omega   (Graph.cpp:579-683).  Range edge k between
+  // translation variables u (source) and v (destination) with range rho and
+  // weight w = weight * precision adds w c c^T on [u, v, r_k] with
+  // c = [-1, +1, rho]  (Q22, Q23, Q33 of Graph.cpp:1137-1141).
   void constructQ() {
     const unsigned dh = d_ + 1;
     std::vector<SparseMatrix::Triplet> trip;
-    trip.reserve(meas_.size() * 4 * dh * dh);
+    trip.reserve(meas_.size() * 4 * dh * dh + ranges_.size() * 9);
     std::vector<double> T(dh * dh), TO(dh * dh), om(dh);
+    auto col = [&](unsigned pose, unsigned a) {
+      return (int32_t)(a < d_ ? rotationColumn(pose, a) : translationColumn(pose));
+    };
     for (const auto &m : meas_) {
       std::fill(T.begin(), T.end(), 0.0);
       for (unsigned a = 0; a < d_; ++a) {
@@ -376,18 +423,28 @@ class Graph {
       om[d_] = m.weight * m.tau;
       for (unsigned a = 0; a < dh; ++a)
         for (unsigned c = 0; c < dh; ++c) TO[a * dh + c] = T[a * dh + c] * om[c];
-      const int32_t i0 = m.p1 * dh, j0 = m.p2 * dh;
       for (unsigned a = 0; a < dh; ++a)
         for (unsigned c = 0; c < dh; ++c) {
           double s = 0.0;
           for (unsigned e = 0; e < dh; ++e) s += TO[a * dh + e] * T[c * dh + e];
-          if (s != 0.0) trip.push_back({(int32_t)(i0 + a), (int32_t)(i0 + c), s});
+          if (s != 0.0) trip.push_back({col(m.p1, a), col(m.p1, c), s});
           if (TO[a * dh + c] != 0.0) {
-            trip.push_back({(int32_t)(i0 + a), (int32_t)(j0 + c), -TO[a * dh + c]});
-            trip.push_back({(int32_t)(j0 + c), (int32_t)(i0 + a), -TO[a * dh + c]});
+            trip.push_back({col(m.p1, a), col(m.p2, c), -TO[a * dh + c]});
+            trip.push_back({col(m.p2, c), col(m.p1, a), -TO[a * dh + c]});
           }
         }
-      for (unsigned a = 0; a < dh; ++a) trip.push_back({(int32_t)(j0 + a), (int32_t)(j0 + a), om[a]});
+      for (unsigned a = 0; a < dh; ++a) trip.push_back({col(m.p2, a), col(m.p2, a), om[a]});
+    }
+    for (size_t e = 0; e < ranges_.size(); ++e) {
+      const RangeMeasurement &rg = ranges_[e];
+      const int32_t idx[3] = {
+          (int32_t)(rg.landmark1 ? landmarkColumn(rg.p1) : translationColumn(rg.p1)),
+          (int32_t)(rg.landmark2 ? landmarkColumn(rg.p2) : translationColumn(rg.p2)),
+          (int32_t)unitSphereColumn((unsigned)e)};
+      const double c[3] = {-1.0, 1.0, rg.range};
+      const double w = rg.weight * rg.precision;
+      for (int a = 0; a < 3; ++a)
+        for (int b2 = 0; b2 < 3; ++b2) trip.push_back({idx[a], idx[b2], w * c[a] * c[b2]});
     }
     Q_ = std::make_shared<SparseMatrix>(SparseMatrix::fromTriplets(k(), k(), std::move(trip)));
   }
@@ -396,6 +453,7 @@ class Graph {
   unsigned n_ = 0, l_ = 0, b_ = 0;
   GraphType type_;
   std::vector<RelativePosePoseMeasurement> meas_;
+  std::vector<RangeMeasurement> ranges_;
   std::shared_ptr<SparseMatrix> Q_;
   std::shared_ptr<Matrix> G_;
   unsigned long version_ = 0;

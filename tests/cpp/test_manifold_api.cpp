@@ -174,6 +174,76 @@ int main() {
     EXPECT(std::fabs(problem.f(Xs) - res.fOpt) <= 1e-10 * std::fabs(res.fOpt) + 1e-14, "fOpt is f(Xopt)");
     EXPECT(std::fabs(res.fInit - f_ref) <= 1e-12 * std::fabs(f_ref), "fInit is f(X0)");
   }
+  // ---------------- range-aided graph: noiseless measurements, ground truth is optimal
+  // (what tests/testAgent.cpp:101-242 asserts on data/range_aided_slam_test_3d.pyfg)
+  {
+    const unsigned d = 3, n = 9, r = 5;
+    std::mt19937_64 rng(11);
+    std::normal_distribution<double> N(0.0, 1.0);
+    std::vector<std::vector<double>> Rg(n, std::vector<double>(9)), tg(n, std::vector<double>(3));
+    for (unsigned i = 0; i < n; ++i) {
+      double q[4] = {N(rng), N(rng), N(rng), N(rng)};
+      const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      DCORA::detail::quat_to_rot(q[0] / nq, q[1] / nq, q[2] / nq, q[3] / nq, Rg[i].data());
+      for (double &t : tg[i]) t = 3.0 * N(rng);
+    }
+    std::vector<DCORA::RelativePosePoseMeasurement> pp;
+    for (unsigned i = 0; i < n; ++i)
+      for (unsigned hop = 1; hop <= 2; ++hop) {
+        const unsigned j = (i + hop) % n;
+        DCORA::RelativePosePoseMeasurement m;
+        m.p1 = i; m.p2 = j; m.d = d; m.kappa = 40.0; m.tau = 7.0;
+        for (unsigned a = 0; a < 3; ++a) {            // R_ij = R_i^T R_j, t_ij = R_i^T (t_j - t_i)
+          for (unsigned c = 0; c < 3; ++c) {
+            double sacc = 0.0;
+            for (unsigned e = 0; e < 3; ++e) sacc += Rg[i][e * 3 + a] * Rg[j][e * 3 + c];
+            m.R[a * 3 + c] = sacc;
+          }
+          double st = 0.0;
+          for (unsigned e = 0; e < 3; ++e) st += Rg[i][e * 3 + a] * (tg[j][e] - tg[i][e]);
+          m.t[a] = st;
+        }
+        pp.push_back(m);
+      }
+    std::vector<DCORA::RangeMeasurement> rgs;
+    for (unsigned i = 0; i < n; i += 2) {
+      DCORA::RangeMeasurement g2;
+      g2.p1 = i; g2.p2 = (i + 4) % n; g2.precision = 25.0;
+      double s2 = 0.0;
+      for (unsigned e = 0; e < 3; ++e) s2 += (tg[g2.p1][e] - tg[g2.p2][e]) * (tg[g2.p1][e] - tg[g2.p2][e]);
+      g2.range = std::sqrt(s2);
+      rgs.push_back(g2);
+    }
+    auto graph = std::make_shared<DCORA::Graph>(0, r, d, DCORA::GraphType::RangeAidedSLAMGraph);
+    graph->setMeasurements(pp, rgs);
+    DCORA::QuadraticProblem problem(graph);
+    Matrix X(r, graph->k());
+    for (unsigned i = 0; i < n; ++i) {
+      for (unsigned c = 0; c < 3; ++c)
+        for (unsigned e = 0; e < 3; ++e) X(e, graph->rotationColumn(i, c)) = Rg[i][e * 3 + c];
+      for (unsigned e = 0; e < 3; ++e) X(e, graph->translationColumn(i)) = tg[i][e];
+    }
+    for (size_t k2 = 0; k2 < rgs.size(); ++k2)
+      for (unsigned e = 0; e < 3; ++e)
+        X(e, graph->unitSphereColumn((unsigned)k2)) =
+            (tg[rgs[k2].p1][e] - tg[rgs[k2].p2][e]) / rgs[k2].range;
+    EXPECT(graph->k() == 4 * n + rgs.size() && !problem.useSEManifold(), "RA graph dimensions");
+    EXPECT(std::fabs(problem.f(X)) < 1e-9, "RA graph: f(ground truth) = 0");
+    EXPECT(problem.RieGradNorm(X) < 1e-7, "RA graph: ground truth is a critical point");
+    DCORA::ROptParameters prm;
+    prm.time_bound_s = 0;
+    DCORA::QuadraticOptimizer opt(&problem, prm);
+    const Matrix Xs = opt.optimize(X);
+    double e_fix = 0.0;
+    for (size_t j = 0; j < X.cols(); ++j)
+      for (unsigned q = 0; q < r; ++q) e_fix = std::max(e_fix, std::fabs(Xs(q, j) - X(q, j)));
+    EXPECT(e_fix < 1e-9, "RA graph: optimize() keeps the ground truth fixed");
+    double theta = 0.0;
+    DCORA::Vector v;
+    DCORA::CertificateInfo info;
+    const bool ok = DCORA::fastVerification(problem, X, 1e-4, &theta, &v, &info);
+    EXPECT(ok && info.lambda_min > -1e-6, "RA graph: ground truth is certified");
+  }
   std::printf(failures ? "FAILED %d checks\n" : "all checks passed\n", failures);
   return failures ? 1 : 0;
 }
