@@ -11,7 +11,10 @@ pytestmark = pytest.mark.gpu
 
 CASES = [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 4), ("torus3D", 6),
          ("city10000", 3), ("kitti_00", 5), ("range_aided_slam_test_2d", 2),
-         ("range_aided_slam_test_3d", 5), ("tiers", 3), ("tiers", 7)]
+         ("range_aided_slam_test_3d", 5), ("tiers", 3), ("tiers", 7),
+         # high staircase ranks: every kernel is templated on r = 1..16
+         ("smallGrid3D", 9), ("smallGrid3D", 16), ("range_aided_slam_test_2d", 8),
+         ("range_aided_slam_test_3d", 12)]
 
 
 @pytest.fixture(scope="module", params=CASES, ids=[f"{n}-r{r}" for n, r in CASES])

@@ -35,6 +35,7 @@ def test_ground_truth_is_a_fixed_point(name):
 
 
 @pytest.mark.parametrize("name,r,tol,iters", [("smallGrid3D", 5, 1e-6, 300),
+                                              ("smallGrid3D", 9, 1e-6, 300),
                                               ("tinyGrid3D", 4, 1e-7, 300),
                                               ("range_aided_slam_test_3d", 5, 1e-7, 3000)])
 def test_rtr_converged_cost_matches_oracle(name, r, tol, iters):
