@@ -480,15 +480,17 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       DCORA_LAUNCH_CHECK(p);
       pt.mark(2);
       ++n_inner_done;
+      // how many agents go on?  Read before the preconditioner so that the last
+      // iteration (the usual case: tCG ends for every agent of the colour at once)
+      // does not launch a K5 / projection / stepC / update that would exit at once
+      DCORA_TRY(read_counters(p, cnt));
+      n_tcg = cnt[1];
+      if (n_tcg == 0) { pt.mark(3); break; }
       DCORA_TRY(launch_precond(p, x1, r, z, F_TCG, nullptr, 0, r));  // + <z, r>
       tcg_stepC_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       // delta = -z + beta * delta
       DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, S_BETA, 1.0, delta, F_TCG));
-      if (j + 1 < prm->RTR_tCG_iterations) {   // else the loop ends anyway
-        DCORA_TRY(read_counters(p, cnt));
-        n_tcg = cnt[1];
-      }
       pt.mark(3);
     }
     // ---- candidate, model decrease, rho (SolversTR::Run)

@@ -146,7 +146,7 @@ template <int R, int DH, int CL, int MODE>
 __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
                                           const double *__restrict__ V, double *T,
                                           double *Y, double *OUT,
-                                          unsigned long long *&trace) {
+                                          unsigned long long *&trace, double *scratch) {
   constexpr int BS = DH * DH;
   constexpr int ITW = 4 + 8 * BS;  // words per phase-A iteration
   const int lane = rd.lane;
@@ -291,6 +291,14 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
 #pragma unroll
         for (int q = 0; q < R; ++q) tv[q] = src[q];
       }
+      // the block's right-hand side goes through this warp's shared scratch: row j is
+      // then a broadcast read (R shared loads) instead of 2 R shuffles per column
+      __syncwarp();
+      if (lane < w) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) scratch[lane * R + q] = tv[q];
+      }
+      __syncwarp();
       rd.ensure(pos + w * (w + 1) / 2);  // the whole packed triangle (<= 528 words)
       {
         int off = pos;
@@ -305,7 +313,7 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
             off += j + 1;
           }
 #pragma unroll
-          for (int q = 0; q < R; ++q) acc[q] = fma(m, __shfl_sync(0xffffffffu, tv[q], j), acc[q]);
+          for (int q = 0; q < R; ++q) acc[q] = fma(m, scratch[j * R + q], acc[q]);
         }
         pos = off;
       }
@@ -382,6 +390,8 @@ trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
   extern __shared__ __align__(128) unsigned long long trsv_smem[];
   unsigned long long *ring = trsv_smem + warp * RING_WORDS;
   unsigned long long *mbar = trsv_smem + TRSV_NW * RING_WORDS + warp * NCH;
+  double *scratch = reinterpret_cast<double *>(trsv_smem + TRSV_NW * (RING_WORDS + NCH)) +
+                    warp * (TRSV_SMALL_BLOCK * R);
   const size_t wi = (size_t)agent * nwarps + gwarp;
   TapeReader rd;
   rd.init(tape + tape_off[wi], tape_chunks[wi], ring, mbar, lane);
@@ -391,8 +401,8 @@ trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
       (trace_buf && agent == trace_agent && gwarp == 0 && lane == 0) ? trace_buf : nullptr;
   if (trace) *trace++ = globaltimer_ns();
   int pos = 0;
-  trsv_walk<R, DH, CL, 0>(rd, pos, nlev[agent * 2 + 0], V, T, Y, OUT, trace);
-  trsv_walk<R, DH, CL, 1>(rd, pos, nlev[agent * 2 + 1], V, T, Y, OUT, trace);
+  trsv_walk<R, DH, CL, 0>(rd, pos, nlev[agent * 2 + 0], V, T, Y, OUT, trace, scratch);
+  trsv_walk<R, DH, CL, 1>(rd, pos, nlev[agent * 2 + 1], V, T, Y, OUT, trace, scratch);
   if (trace) *trace = 0ull;
   rd.drain();
 }
@@ -474,10 +484,15 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
   if (as && as->n_agents == 0) return DCORA_OK;
   cfg.gridDim = dim3((unsigned)((as ? as->n_agents : M.A) * CL));
   cfg.blockDim = dim3(TRSV_THREADS);
-  cfg.dynamicSmemBytes = TRSV_SMEM;
+  constexpr int smem_bytes = TRSV_SMEM + TRSV_NW * TRSV_SMALL_BLOCK * R * 8;  // + scratch
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = p->stream;
-  DCORA_CUDA(cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+  static unsigned attr_done = 0;  // per instantiation: bit d = set on device d
+  if (M.device >= 32 || !(attr_done & (1u << M.device))) {
+    DCORA_CUDA(cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (M.device < 32) attr_done |= 1u << M.device;
+  }
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
