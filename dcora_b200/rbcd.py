@@ -160,7 +160,8 @@ class RBCD:
 
     def __init__(self, gp: GlobalProblem, r: int, rank=0, world=1, device=0,
                  params: ROptParameters | None = None, precond=True, group=None,
-                 plan: RankPlan | None = None, diag=None):
+                 plan: RankPlan | None = None, diag=None, acceleration=False,
+                 restart_interval=30):
         import torch
         self.torch = torch
         self.gp, self.r, self.rank, self.world, self.group = gp, r, rank, world, group
@@ -187,6 +188,15 @@ class RBCD:
             self.H = torch.zeros((world * plan.seg_cols, r), dtype=torch.float64, device=self.device)
             self.sendbuf = torch.zeros((plan.seg_cols, r), dtype=torch.float64, device=self.device)
         self.agent_updates = 0
+        # RBCD++ (Nesterov acceleration, Agent.cpp:535-596,1158-1214; AgentParameters
+        # acceleration / restartInterval, Agent.h:40-185)
+        self.acc = bool(acceleration)
+        self.restart_interval = int(restart_interval)
+        self.it = 0
+        if self.acc:
+            # several iterate-sized buffers (X, Y, V, XPrev) are exchanged per step:
+            # no single tracked buffer
+            self.P.set_iterate_tracking(False)
 
     # -- state ---------------------------------------------------------------
     def set_X(self, X_global):
@@ -199,7 +209,13 @@ class RBCD:
     def set_device_X(self, X_dev):
         """Replace the iterate by a device tensor (K_local, r) written by the caller."""
         self.X = X_dev
-        self.P.set_iterate_tracking(True)      # forget the tracked copy
+        if self.acc:                            # initializeAcceleration (Agent.cpp:1178-1187)
+            self.V = X_dev.clone()
+            self.Y = X_dev.clone()
+            self.gamma = 0.0
+            self.alpha = 0.0
+        else:
+            self.P.set_iterate_tracking(True)   # forget the tracked copy
 
     def get_X(self):
         """numpy (r, K_local)."""
@@ -218,11 +234,44 @@ class RBCD:
     def iterate(self):
         for c in range(self.plan.num_colors):
             active = (self.local_colors == c).astype(np.uint8)
+            if self.acc:
+                self._accelerated_step(active)
+                continue
             self.exchange()
             if active.any():
                 self.P.update_G(self.X, self.H, active)
                 self.X = self.opt.optimize(self.X, active, out=self.X)
                 self.agent_updates += int(active.sum())
+
+    def _accelerated_step(self, active):
+        """One driver iteration of RBCD++: the agents in `active` run
+        Agent::iterate(true), all others iterate(false) (Agent.cpp:535-596).  The
+        drivers hand X (not Y) to the selected agent as auxiliary neighbour states
+        (MultiRobotExample.cpp:247-258), so G is built from the previous iterate."""
+        N = self.gp.A
+        self.it += 1
+        self.exchange()                                   # public columns of XPrev = X
+        Xprev = self.X.clone()
+        self.gamma = (1 + np.sqrt(1 + 4 * N ** 2 * self.gamma ** 2)) / (2 * N)   # updateGamma
+        self.alpha = 1 / (self.gamma * N)                                       # updateAlpha
+        # updateY: Y = projectToManifold((1 - alpha) X + alpha V), every agent
+        Y = self.P.combine_project(1 - self.alpha, self.X, self.alpha, self.V, None)
+        Xn = Y.clone()                                    # iterate(false): X = Y
+        if active.any():
+            self.P.update_G(Xprev, self.H, active)
+            Xn = self.opt.optimize(Y, active, out=Xn)
+            self.agent_updates += int(active.sum())
+        # updateV: V = projectToManifold(V + gamma (X - Y))
+        V = self.P.combine_project(1.0, self.V, self.gamma, Xn - Y, None)
+        self.X, self.V, self.Y = Xn, V, Y
+        if (self.it + 1) % self.restart_interval == 0:    # shouldRestart / restartNesterov...
+            Xr = Xprev.clone()
+            if active.any():
+                self.P.update_G(Xprev, self.H, active)
+                Xr = self.opt.optimize(Xprev, active, out=Xr)
+            self.X, self.V, self.Y = Xr, Xr.clone(), Xr.clone()
+            self.gamma = 0.0
+            self.alpha = 0.0
 
     def monitor(self):
         """Global cost f and Riemannian gradient norm (the centralised

@@ -149,3 +149,48 @@ def test_iterate_tracking_does_not_change_results(name, robots):
     H2.iterate()
     assert np.array_equal(G.get_X(), H2.get_X())
     assert not np.array_equal(G.get_X(), Xa)
+
+
+@pytest.mark.parametrize("name,robots", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 2)])
+def test_combine_project_is_the_nesterov_building_block(name, robots):
+    # K9: OUT = projectToManifold(a A + b B) for the active agents, OUT = A for the others
+    # (Agent::updateY / updateV, Agent.cpp:1202-1214; projectToSEMatrix / RAMatrix)
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup(name, robots, r)
+    G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0))
+    A = _random_X(blocks, r, gp.K, 3)
+    B = np.random.default_rng(4).standard_normal((r, gp.K))
+    active = np.zeros(robots, np.uint8)
+    active[::2] = 1
+    out = G.P.combine_project(0.7, A, 0.3, B, active)
+    for a, b in enumerate(blocks):
+        s = slice(b.c0, b.c1)
+        ref = mf.project_manifold(b.L, 0.7 * A[:, s] + 0.3 * B[:, s]) if active[a] else A[:, s]
+        assert rel_err(out[:, s], ref) < 1e-12
+
+
+def test_accelerated_sweeps_follow_the_oracle():
+    # RBCD++ with restart (Agent.cpp:535-596,1158-1214) on smallGrid3D / 5 robots
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup("smallGrid3D", 5, r)
+    X0 = _random_X(blocks, r, gp.K, 6)
+    G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0), acceleration=True,
+                  restart_interval=7)
+    for a, b in enumerate(blocks):
+        b.P.reg = G.P.precond_reg(a)
+    O = orbcd.RBCD(blocks, cross, solver.ROptParameters(), acceleration=True, restart_interval=7)
+    G.set_X(X0)
+    O.set_X(X0)
+    colors = G.plan.colors
+    for it in range(4):                       # 4 sweeps x colours > restart interval
+        G.iterate()
+        O.sweep(colors)
+        assert rel_err(G.get_X(), O.X) < 1e-6, it
+    assert G.it == O.it and abs(G.gamma - O.gamma) < 1e-12
+    f_g, g_g = G.monitor()
+    f_o, g_o = O.monitor()
+    assert abs(f_g - f_o) <= 1e-7 * abs(f_o)
