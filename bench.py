@@ -353,7 +353,7 @@ def run_ours(args):
             out["e2e"] = e2e
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -493,11 +493,40 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
+
+
+class _StdoutToStderr:
+    """Everything written to fd 1 while the benchmark runs (e.g. the NCCL version banner
+    of the first communicator) goes to stderr, so that stdout carries exactly ONE JSON
+    line; `emit` restores fd 1 for that line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
+_OUT = None
+
+
+def emit_json(obj):
+    text = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 if __name__ == "__main__":
     a = parse()
+    _OUT = _StdoutToStderr()
     if a.impl == "reference":
         run_reference(a)
     else:
