@@ -194,3 +194,42 @@ def test_accelerated_sweeps_follow_the_oracle():
     f_g, g_g = G.monitor()
     f_o, g_o = O.monitor()
     assert abs(f_g - f_o) <= 1e-7 * abs(f_o)
+
+
+def test_distributed_certificate_matches_the_centralised_one():
+    # SURVEY 8e (certification): S = Q - Lambda applied through the agents' diagonal blocks +
+    # the coupling product + halo exchange, lambda_min by block Rayleigh-Ritz; compared with
+    # dcora_certify on a single handle holding the global Q, at a saddle and at the optimum
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    from dcora_b200.certify_dist import certify_distributed
+    from tests.common import central_problem, gpu_problem
+    # (a) rank-3 saddle of the centralised problem (see test_gpu_solver)
+    P3, g, info = central_problem("smallGrid3D", 3)
+    gp3 = gpu_problem(P3)
+    X0 = mf.random_point(P3.L, np.random.default_rng(7))
+    go = dc.QuadraticOptimizer(gp3, dc.ROptParameters(time_bound_s=0.0, RTR_iterations=300,
+                                                      RTR_tCG_iterations=500, gradnorm_tol=1e-6))
+    Xs = go.optimize(X0)
+    cen, _ = gp3.certify(Xs, 1e-3, tol=1e-10)
+    gp, blocks, cross = _setup("smallGrid3D", 5, 3)
+    G = rbcd.RBCD(gp, 3, params=dc.ROptParameters(time_bound_s=0.0))
+    G.set_X(Xs)                      # contiguous partition: agent-major == pose order
+    f_before = G.monitor()
+    res = certify_distributed(G, 1e-3, tol=1e-10)
+    assert res.converged and res.is_psd == bool(cen.is_psd)
+    assert abs(res.lambda_min - cen.lambda_min) <= 1e-6 * max(abs(cen.lambda_min), 1e-3)
+    assert G.monitor() == f_before   # the RBCD state (linear term, iterate) is restored
+    # (b) the certified optimum at rank 5
+    P5, g, info = central_problem("smallGrid3D", 5)
+    gp5 = gpu_problem(P5)
+    go = dc.QuadraticOptimizer(gp5, dc.ROptParameters(time_bound_s=0.0, RTR_iterations=300,
+                                                      RTR_tCG_iterations=500, gradnorm_tol=1e-7))
+    Xo = go.optimize(mf.random_point(P5.L, np.random.default_rng(1)))
+    cen, _ = gp5.certify(Xo, 1e-3, tol=1e-10)
+    gp, blocks, cross = _setup("smallGrid3D", 5, 5)
+    G = rbcd.RBCD(gp, 5, params=dc.ROptParameters(time_bound_s=0.0))
+    G.set_X(Xo)
+    res = certify_distributed(G, 1e-3, tol=1e-10)
+    assert res.is_psd and bool(cen.is_psd)
+    assert abs(res.lambda_min - cen.lambda_min) <= 1e-6 * max(abs(cen.lambda_min), 1e-3)
