@@ -702,6 +702,164 @@ class QuadraticOptimizer {  // QuadraticOptimizer.h:25-147
   ROPTResult result_;
 };
 
+// ----------------------------------------------------------------- AgentBatch
+// All agents that live on one GPU as ONE batched handle: the device-side state
+// behind a set of DCORA::Agent objects of one process (include/DCORA/Agent.h).
+// Built from the data matrix of the whole (pose-graph) problem and a contiguous
+// partition of the poses over agents (the rule of examples/MultiRobotExample.cpp:
+// 56-118): agent a owns the diagonal block Q[a,a] -- what its own Graph builds from
+// its private edges and the owned endpoints of its shared edges (Graph.cpp:579-622)
+// -- and the off-diagonal blocks become the coupling that turns the neighbours'
+// public poses into the linear term G (Graph::constructLinearCostTermPGO, :685-822).
+// One RBCD step of a set of mutually non-adjacent agents is
+//     updateLinearTerms(X, active);  optimize(&X, active, params);
+// i.e. Agent::updateNeighborStates + Agent::iterate(true) (Agent.cpp:535-596,844-906)
+// for every active agent at once.
+class AgentBatch {
+ public:
+  AgentBatch(const SparseMatrix &Qglobal, const std::vector<unsigned> &poses_per_agent,
+             unsigned r, unsigned d, double precond_reg = 0.1, int device = 0)
+      : r_(r), d_(d) {
+    const unsigned dh = d + 1;
+    const int A = (int)poses_per_agent.size();
+    coff_.assign(A + 1, 0);
+    for (int a = 0; a < A; ++a) coff_[a + 1] = coff_[a] + (int64_t)dh * poses_per_agent[a];
+    DCORA_B200_CHECK(coff_[A] == Qglobal.rows && Qglobal.rows == Qglobal.cols,
+                     "partition does not cover the data matrix");
+    std::vector<int32_t> agent_of_col(Qglobal.rows);
+    for (int a = 0; a < A; ++a)
+      for (int64_t c = coff_[a]; c < coff_[a + 1]; ++c) agent_of_col[c] = a;
+    // split Q into the agents' diagonal blocks and the cross-agent remainder
+    std::vector<SparseMatrix> diag(A);
+    for (int a = 0; a < A; ++a) {
+      diag[a].rows = diag[a].cols = (int32_t)(coff_[a + 1] - coff_[a]);
+      diag[a].rowptr.assign(diag[a].rows + 1, 0);
+    }
+    cross_.rows = cross_.cols = Qglobal.rows;
+    cross_.rowptr.assign(Qglobal.rows + 1, 0);
+    adjacency_.assign(A, std::vector<int>());
+    for (int32_t row = 0; row < Qglobal.rows; ++row) {
+      const int a = agent_of_col[row];
+      const int32_t lr = (int32_t)(row - coff_[a]);
+      for (int32_t p = Qglobal.rowptr[row]; p < Qglobal.rowptr[row + 1]; ++p) {
+        const int32_t c = Qglobal.col[p];
+        const int b = agent_of_col[c];
+        if (b == a) {
+          diag[a].col.push_back((int32_t)(c - coff_[a]));
+          diag[a].val.push_back(Qglobal.val[p]);
+        } else {
+          cross_.col.push_back(c);
+          cross_.val.push_back(Qglobal.val[p]);
+          if (std::find(adjacency_[a].begin(), adjacency_[a].end(), b) == adjacency_[a].end())
+            adjacency_[a].push_back(b);
+        }
+      }
+      diag[a].rowptr[lr + 1] = (int32_t)diag[a].col.size();
+      cross_.rowptr[row + 1] = (int32_t)cross_.col.size();
+    }
+    std::vector<dcora_agent_desc> desc(A);
+    for (int a = 0; a < A; ++a) {
+      desc[a].n = (int32_t)poses_per_agent[a]; desc[a].l = 0; desc[a].b = 0;
+      desc[a].rowptr = diag[a].rowptr.data();
+      desc[a].col = diag[a].col.data();
+      desc[a].val = diag[a].val.data();
+      desc[a].G = nullptr;
+      desc[a].precond_reg = precond_reg;
+    }
+    h_ = std::make_shared<detail::Handle>();
+    DCORA_B200_CALL(dcora_problem_create(desc.data(), A, (int32_t)r, (int32_t)d, DCORA_ORDER_SE,
+                                         device, &h_->p));
+    DCORA_B200_CALL(dcora_problem_set_coupling(h_->p, nullptr, 0, cross_.rowptr.data(),
+                                               cross_.col.data(), cross_.val.data()));
+  }
+  int numAgents() const { return (int)coff_.size() - 1; }
+  int64_t problemDimension() const { return coff_.back(); }
+  // agents sharing at least one measurement with agent a
+  const std::vector<int> &neighbors(int a) const { return adjacency_[a]; }
+  // Greedy colouring of the agent graph (largest degree first): agents of one colour share no
+  // measurement and may take their RBCD step at the same time.
+  std::vector<int> coloring() const {
+    const int A = numAgents();
+    std::vector<int> order(A), color(A, -1);
+    for (int a = 0; a < A; ++a) order[a] = a;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return adjacency_[x].size() > adjacency_[y].size();
+    });
+    for (int a : order) {
+      int c = 0;
+      for (bool clash = true; clash; ++c) {
+        clash = false;
+        for (int b : adjacency_[a]) clash = clash || color[b] == c;
+        if (!clash) break;
+      }
+      color[a] = c;
+    }
+    return color;
+  }
+  // G_a = sum over the neighbours of a of X_nbr * (cross block)  for the active agents
+  void updateLinearTerms(const Matrix &X, const std::vector<uint8_t> &active) {
+    check(X);
+    DCORA_B200_CALL(dcora_problem_update_G(h_->p, X.data(), nullptr, mask(active)));
+  }
+  // QuadraticOptimizer::optimize of every active agent, in place
+  std::vector<ROPTResult> optimize(Matrix *X, const std::vector<uint8_t> &active,
+                                   const ROptParameters &params = ROptParameters()) {
+    check(*X);
+    dcora_ropt_params cp;
+    dcora_ropt_params_default(&cp);
+    cp.method = params.method == ROptParameters::ROptMethod::RTR ? 0 : 1;
+    cp.gradnorm_tol = params.gradnorm_tol;
+    cp.RGD_stepsize = params.RGD_stepsize;
+    cp.RGD_use_preconditioner = params.RGD_use_preconditioner;
+    cp.RTR_iterations = params.RTR_iterations;
+    cp.RTR_tCG_iterations = params.RTR_tCG_iterations;
+    cp.RTR_initial_radius = params.RTR_initial_radius;
+    cp.time_bound_s = params.time_bound_s;
+    cp.retraction = params.retraction;
+    std::vector<dcora_ropt_result> cr(numAgents());
+    DCORA_B200_CALL(dcora_rtr_solve(h_->p, X->data(), X->data(), &cp, mask(active), cr.data()));
+    std::vector<ROPTResult> out;
+    for (const auto &c : cr) {
+      ROPTResult res(c.success != 0, c.fInit, c.gradNormInit, c.fOpt, c.gradNormOpt, c.elapsedMs);
+      res.tCGStatus = (ROPTLIB::tCGstatusSet)c.tCGStatus;
+      res.outerIterations = c.outer_iterations;
+      res.innerIterations = c.inner_iterations;
+      out.push_back(res);
+    }
+    return out;
+  }
+  // cost of the partitioned problem and norm of its Riemannian gradient: the centralised
+  // evaluation the drivers do every iteration (MultiRobotExample.cpp:264-281), blockwise.
+  // The linear terms must be current for ALL agents (updateLinearTerms(X, {})).
+  void evaluate(const Matrix &X, double *cost, double *gradnorm) {
+    check(X);
+    const int A = numAgents();
+    std::vector<double> quad(A), lin(A), gn(A);
+    DCORA_B200_CALL(dcora_problem_cost_terms(h_->p, X.data(), quad.data(), lin.data()));
+    DCORA_B200_CALL(dcora_problem_rgradnorm(h_->p, X.data(), gn.data()));
+    double f = 0.0, g2 = 0.0;
+    for (int a = 0; a < A; ++a) { f += quad[a] + 0.5 * lin[a]; g2 += gn[a] * gn[a]; }
+    if (cost) *cost = f;
+    if (gradnorm) *gradnorm = std::sqrt(g2);
+  }
+  dcora_problem *handle() const { return h_->p; }
+
+ private:
+  const uint8_t *mask(const std::vector<uint8_t> &active) const {
+    if (active.empty()) return nullptr;
+    DCORA_B200_CHECK((int)active.size() == numAgents(), "one flag per agent");
+    return active.data();
+  }
+  void check(const Matrix &X) const {
+    DCORA_B200_CHECK(X.rows() == r_ && (int64_t)X.cols() == coff_.back(), "X must be r x K");
+  }
+  unsigned r_, d_;
+  std::vector<int64_t> coff_;
+  SparseMatrix cross_;
+  std::vector<std::vector<int>> adjacency_;
+  std::shared_ptr<detail::Handle> h_;
+};
+
 // ------------------------------------------------------------ certification
 // fastVerification (DCORA_utils.cpp:1713-1735) on the certificate of X:
 // S = Q - Lambda(X) (constructDualCertificateMatrix{PGO,RASLAM}, :1898-1982) is

@@ -76,3 +76,41 @@ def test_cpp_manifold_and_problem_api(exe):
     out = subprocess.run([binary], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "all checks passed" in out.stdout and "FAILED" not in out.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_rbcd_driver_reaches_the_known_optimum(exe, tmp_path):
+    # examples/rbcd_pgo.cpp: DCORA::AgentBatch (batched agents + coupling) driven from C++;
+    # smallGrid3D / 5 robots (BASELINE.json configs[0]) must reach 2 f* = 1025.398052
+    binary = os.path.join(os.path.dirname(exe), "rbcd_pgo")
+    meas, info = load_golden("smallGrid3D")
+    path = tmp_path / "smallGrid3D.g2o"
+    write_g2o(path, meas, "smallGrid3D")
+    # stop rule of the reference driver (centralised gradnorm < 0.1, MultiRobotExample.cpp:
+    # 283-286); the agents' own default tolerance (1e-2) bounds what RBCD can reach
+    out = subprocess.run([binary, str(path), "5", "--tol", "0.05", "--iters", "600"],
+                         capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    s = lines[-1]
+    assert s["summary"] and s["robots"] == 5 and s["gradnorm"] < 0.05
+    assert abs(s["cost_2f"] - 1025.3980521) < 1e-3
+    costs = [l["cost_2f"] for l in lines if "iter" in l]
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))      # monotone descent
+
+
+@pytest.mark.gpu
+def test_cpp_rbcd_driver_on_kitti_with_64_agents(exe, tmp_path):
+    # configs[3] partition: kitti_00 split into 64 contiguous agents; a few sweeps must
+    # decrease the cost monotonically (the C++ path end to end: reader, Q, split, coupling)
+    binary = os.path.join(os.path.dirname(exe), "rbcd_pgo")
+    meas, info = load_golden("kitti_00")
+    path = tmp_path / "kitti_00.g2o"
+    write_g2o(path, meas, "kitti_00")
+    out = subprocess.run([binary, str(path), "64", "--tol", "1e-9", "--iters", "31"],
+                         capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines and lines[-1]["summary"] and lines[-1]["robots"] == 64, out.stdout + out.stderr
+    costs = [l["cost_2f"] for l in lines if "iter" in l]
+    assert len(costs) >= 3 and all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))
+    assert costs[-1] < 0.5 * costs[0]
