@@ -256,6 +256,15 @@ class QuadraticProblem:
     def PreCondition(self, X, V):
         return self._binary(self.lib.dcora_problem_precond, X, V)
 
+    def factor_solve(self, V):
+        """(Q + reg I)^-1 V per agent (the preconditioner's Cholesky solve without the
+        tangent projection: dcora_problem_precond with X = NULL)."""
+        v = _Arg(V, self.r, self.K)
+        out = _new_out(V, self.r, self.K)
+        o = _Arg(out, self.r, self.K, out=True)
+        check(self.lib.dcora_problem_precond(self.h, None, v.ptr, o.ptr))
+        return out
+
     def Retract(self, X, V, retraction=RETRACT_QF):
         return self._binary(self.lib.dcora_problem_retract, X, V, retraction)
 

@@ -15,7 +15,7 @@ vectors for a right-multiplication by the symmetric Q):
                          here with torch on the device.
 lambda_min is computed like dcora_certify does on one handle (csrc/certify.cu): a Krylov-type
 iteration from a RANDOM start (here block Davidson / Rayleigh-Ritz with block size r and thick
-restart) until its smallest Ritz pair has converged, then a Rayleigh-Ritz step on span(rows of
+restart, residuals preconditioned by the agents' own Cholesky factors = block Jacobi) until its smallest Ritz pair has converged, then a Rayleigh-Ritz step on span(rows of
 X) -- at a critical point they span the null space of S, the cluster a random start resolves
 last -- and the smaller of the two upper bounds is reported.  (The rows of X must NOT seed the
 iteration: they are exact eigenvectors, their Ritz pair "converges" at once and would hide a
@@ -53,7 +53,7 @@ def _local_indices(S):
 
 
 def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
-                        early_exit=False) -> DistCertificate:
+                        early_exit=False, precondition=True) -> DistCertificate:
     """`S` is a dcora_b200.rbcd.RBCD (any world size) holding the iterate; every rank
     calls this collectively and gets the same result."""
     t = S.torch
@@ -177,7 +177,15 @@ def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
             if B.shape[1] + r > smax:            # thick restart on the smallest Ritz vectors
                 kk = min(keep_n, B.shape[1])
                 B, SB = B @ Y[:, :kk], SB @ Y[:, :kk]
-            W = orthonormalise(Rr, B)
+            # Davidson correction: the residuals through the agents' Cholesky factors
+            # (block-Jacobi (Q_aa + reg I)^-1: the Laplacian part of S that makes a plain
+            # Krylov iteration slow), then orthonormalised against the basis
+            Wc = Rr
+            if precondition and P.factor_nnz() > 0:
+                if b < r:
+                    Wc = t.cat([Rr, t.zeros((K, r - b), dtype=f64, device=dev)], 1)
+                Wc = P.factor_solve(Wc.contiguous())[:, :b]
+            W = orthonormalise(Wc, B)
             if W.shape[1] == 0:
                 conv = True
                 break

@@ -425,9 +425,9 @@ int dcora_problem_precond(dcora_problem *p, const double *X, const double *V,
   DCORA_ENTER(p);
   double *x = p->vec(WS_IO0), *v = p->vec(WS_IO1), *o = p->vec(WS_IO2);
   if (!x || !v || !o) return DCORA_ERR_ALLOC;
-  DCORA_TRY(import_matrix(p, X, x, p->r));
+  if (X) DCORA_TRY(import_matrix(p, X, x, p->r));
   DCORA_TRY(import_matrix(p, V, v, p->r));
-  DCORA_TRY(launch_precond(p, x, v, o, -1));
+  DCORA_TRY(launch_precond(p, X ? x : nullptr, v, o, -1));
   return export_matrix(p, o, OUT, p->r);
 }
 

@@ -517,6 +517,7 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
   if (!F.present) {
     // Graph::hasPreconditioner() false: the reference only projects
     // (QuadraticProblem.cpp:78-83)
+    if (!X) return launch_copy(p, OUT, V, mask_flag);
     return launch_project_tangent(p, X, V, OUT, mask_flag, dot_with);
   }
   double *panel = p->vec(WS_TRSV_PANEL);
@@ -531,6 +532,7 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
       default: DCORA_TRY((launch_trsv<R, DH, 8>(p, V, tmp, panel, sol, mask_flag, trace, trace_agent))); break;
     }
   })
+  if (!X) return launch_copy(p, OUT, sol, mask_flag);  // plain (Q + reg I)^-1 V
   return launch_project_tangent(p, X, sol, OUT, mask_flag, dot_with);
 }
 

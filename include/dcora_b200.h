@@ -150,7 +150,10 @@ int dcora_problem_f(dcora_problem *p, const double *X, double *f_out);
 int dcora_problem_egrad(dcora_problem *p, const double *X, double *EG);
 /* QuadraticProblem::EucHessianEta (:61-68): HV = V*Q. */
 int dcora_problem_hessvec(dcora_problem *p, const double *V, double *HV);
-/* QuadraticProblem::PreConditioner (:70-84): proj_X((Q+reg I)^-1 V^T)^T. */
+/* QuadraticProblem::PreConditioner (:70-84): proj_X((Q+reg I)^-1 V^T)^T.
+ * X == NULL: the plain solve (Q+reg I)^-1 V without the tangent projection
+ * (the CHOLMOD solve of :79 alone; used as a block-Jacobi preconditioner by the
+ * distributed certificate). */
 int dcora_problem_precond(dcora_problem *p, const double *X, const double *V,
                           double *OUT);
 /* QuadraticProblem::RieGrad / RieGradNorm (:86-123). */

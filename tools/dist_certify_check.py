@@ -29,7 +29,8 @@ def main():
     for _ in range(5):
         S.iterate()
     f, g = S.monitor()
-    res = certify_distributed(S, 1e-3, tol=1e-10, max_iters=int(os.environ.get('CERT_ITERS', '60')))
+    res = certify_distributed(S, 1e-3, tol=1e-10, max_iters=int(os.environ.get('CERT_ITERS', '60')),
+                              precondition=os.environ.get('CERT_PRECOND', '1') == '1')
     f2, g2 = S.monitor()
     if rank == 0:
         sys.stderr.write(json.dumps({"world": world, "f": f, "gradnorm": g, "lambda_min": res.lambda_min,
