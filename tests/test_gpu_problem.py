@@ -72,6 +72,14 @@ def test_precondition(pair):
     assert rel_err(gp.PreCondition(X, V), ref) < 1e-8
 
 
+def test_factor_solve_without_projection(pair):
+    # dcora_problem_precond with X = NULL: the Cholesky solve (Q + reg I)^-1 V alone
+    # (graph_->preconditioner()->solve, QuadraticProblem.cpp:79)
+    P, gp, X, V = pair
+    ref = P._factor().solve(np.ascontiguousarray(V.T)).T
+    assert rel_err(gp.factor_solve(V), ref) < 1e-8
+
+
 def test_device_resident_arguments(pair):
     torch = pytest.importorskip("torch")
     P, gp, X, V = pair
