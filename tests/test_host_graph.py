@@ -117,3 +117,25 @@ def test_synthetic_grid_is_consistent():
     R0, p0 = Rgt[idx[0, 0, 0]], pos[idx[0, 0, 0]]
     assert np.allclose(R0 @ Ri, Rgt, atol=1e-9)
     assert np.allclose((R0 @ ti.T).T + p0, pos, atol=1e-9)
+
+
+def test_balanced_colouring_is_valid_and_even():
+    # RBCD sweeps colour by colour; every class runs its agents concurrently, so classes must be
+    # independent sets and of even size (one K5 wave per colour on the device)
+    meas, gt, idx = synthetic.grid3d(12, range_fraction=0.1, seed=2)
+    gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, 48))
+    _, cross = gp.split(agents=[])
+    adj = gp.agent_graph(cross)
+    col = pg.greedy_coloring(adj)
+    assert all(col[a] != col[b] for a in range(gp.A) for b in adj[a])
+    sizes = np.bincount(col)
+    raw = -np.ones(gp.A, np.int64)            # the unbalanced greedy colouring, for reference
+    for a in sorted(range(gp.A), key=lambda x: -len(adj[x])):
+        used = {raw[b] for b in adj[a] if raw[b] >= 0}
+        c = 0
+        while c in used:
+            c += 1
+        raw[a] = c
+    assert len(sizes) == raw.max() + 1                   # no colour added
+    assert sizes.max() <= np.bincount(raw).max()         # never worse than greedy
+    assert sizes.max() - sizes.min() <= max(2, np.bincount(raw).max() - np.bincount(raw).min())
