@@ -114,3 +114,43 @@ def test_cpp_rbcd_driver_on_kitti_with_64_agents(exe, tmp_path):
     costs = [l["cost_2f"] for l in lines if "iter" in l]
     assert len(costs) >= 3 and all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))
     assert costs[-1] < 0.5 * costs[0]
+
+
+def _write_measurement_list(path, meas, info):
+    from oracle import dataio
+    pp, rg = meas.pp, meas.rg
+    d = meas.d
+    with open(path, "w") as fh:
+        fh.write(f"D {d}\n")
+        for e in range(len(pp)):
+            vals = list(pp.R[e].reshape(-1)) + list(pp.t[e]) + [pp.kappa[e], pp.tau[e], pp.weight[e]]
+            fh.write(f"PP {pp.p1[e]} {pp.p2[e]} " + " ".join(f"{v:.17g}" for v in vals) + "\n")
+        order = np.argsort(rg.l) if len(rg) else []
+        for e in order:
+            fh.write(f"RG {rg.p1[e]} {rg.p2[e]} {int(rg.type1[e] == dataio.LANDMARK)} "
+                     f"{int(rg.type2[e] == dataio.LANDMARK)} {rg.range[e]:.17g} "
+                     f"{rg.precision[e]:.17g} {rg.weight[e]:.17g}\n")
+        fh.write(f"LM {info['b']}\n")
+
+
+@pytest.mark.parametrize("name", ["range_aided_slam_test_2d", "range_aided_slam_test_3d", "tiers",
+                                  "tinyGrid3D"])
+def test_cpp_graph_data_matrix_matches_oracle(exe, tmp_path, name):
+    # DCORA::Graph::constructQ (pose-pose + range edges, RA ordering [Y | r | p | L]) against the
+    # oracle's Q, which is pinned on the reference's noiseless range-aided fixtures
+    binary = os.path.join(os.path.dirname(exe), "check_graph_q")
+    meas, info = load_golden(name)
+    if len(meas.pl):
+        pytest.skip("pose-landmark relative measurements are not part of the C++ mirror")
+    path = tmp_path / (name + ".txt")
+    _write_measurement_list(path, meas, info)
+    out = subprocess.run([binary, str(path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout.splitlines()[-1])
+    P, g, _ = central_problem(name, info["d"] + 1, use_precond=False)
+    Q = P.Q.tocoo()
+    assert (got["n"], got["l"], got["b"], got["k"]) == (info["n"], info["l"], info["b"], Q.shape[0])
+    fro = float(np.sqrt(np.sum(Q.data ** 2)))
+    chk = float(np.sum(Q.data * np.cos(0.001 * Q.row + 0.002 * Q.col)))
+    assert abs(got["fro"] - fro) <= 1e-12 * fro
+    assert abs(got["checksum"] - chk) <= 1e-10 * fro
