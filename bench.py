@@ -146,19 +146,9 @@ def build_problem(args, log):
 
 
 def initial_X(args, meas, idx, gp):
-    """Spanning-tree guess lifted to rank r with YLift = [I_d; 0]; unit spheres
-    from the guessed translations (sign convention DCORA_utils.cpp:1136-1137)."""
+    """Spanning-tree guess lifted to rank r (dcora_b200.synthetic.lifted_initial_guess)."""
     from dcora_b200 import synthetic
-    R, t = synthetic.spanning_tree_init(meas, args.grid, idx)
-    r, d, n = args.rank, meas.d, meas.n
-    X = np.zeros((r, gp.K))
-    X[:d, gp.rot_cols(np.arange(n)).reshape(-1)] = np.transpose(R, (1, 0, 2)).reshape(d, -1)
-    X[:d, gp.trans_col(np.arange(n))] = t.T
-    if len(meas.rg_i):
-        dv = t[meas.rg_i] - t[meas.rg_j]
-        dv /= np.maximum(np.linalg.norm(dv, axis=1), 1e-12)[:, None]
-        X[:d, gp.sphere_col(np.arange(len(meas.rg_i)))] = dv.T
-    return X
+    return synthetic.lifted_initial_guess(meas, idx, gp, args.grid, args.rank)
 
 
 # --------------------------------------------------------------------------

@@ -153,3 +153,20 @@ def spanning_tree_init(meas: Measurements, S, idx):
     for z in range(1, S):
         step(idx[:, :, z - 1].reshape(-1), idx[:, :, z].reshape(-1))
     return R, t
+
+
+def lifted_initial_guess(meas: Measurements, idx, gp, S, r):
+    """Initial iterate of the synthetic grid: the spanning-tree guess lifted to rank r with
+    YLift = [I_d; 0] (Agent::initialize lifts with a shared YLift, Agent.cpp:502); unit
+    spheres from the guessed translations (sign convention DCORA_utils.cpp:1136-1137).
+    Returns X (r, gp.K) in the reference column ordering of `gp`."""
+    R, t = spanning_tree_init(meas, S, idx)
+    d, n = meas.d, meas.n
+    X = np.zeros((r, gp.K))
+    X[:d, gp.rot_cols(np.arange(n)).reshape(-1)] = np.transpose(R, (1, 0, 2)).reshape(d, -1)
+    X[:d, gp.trans_col(np.arange(n))] = t.T
+    if len(meas.rg_i):
+        dv = t[meas.rg_i] - t[meas.rg_j]
+        dv /= np.maximum(np.linalg.norm(dv, axis=1), 1e-12)[:, None]
+        X[:d, gp.sphere_col(np.arange(len(meas.rg_i)))] = dv.T
+    return X

@@ -7,11 +7,6 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 
-def _bench():
-    import importlib
-    return importlib.import_module("bench")
-
-
 def run(grid, rank=5, range_fraction=0.1, seed=0, tol=1e-4, eta=1e-3, log=print):
     import dcora_b200 as dc
     from dcora_b200 import graph as pg, synthetic
@@ -21,9 +16,7 @@ def run(grid, rank=5, range_fraction=0.1, seed=0, tol=1e-4, eta=1e-3, log=print)
     gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, 1))
     Q = gp.Q()
     t1 = time.perf_counter()
-    a = argparse.Namespace(grid=grid, rank=rank)
-    X0 = sys.modules["__main__"].initial_X(a, meas, idx, gp) if hasattr(
-        sys.modules["__main__"], "initial_X") else _bench().initial_X(a, meas, idx, gp)
+    X0 = synthetic.lifted_initial_guess(meas, idx, gp, grid, rank)
     ag = dc.AgentData(n=int(gp.n_a[0]), l=int(gp.l_a[0]), b=int(gp.b_a[0]), Q=Q,
                       precond_reg="auto_ra" if gp.ra else 0.1)
     P = dc.QuadraticProblem(ag, rank, gp.d, dc.ORDER_RA if gp.ra else dc.ORDER_SE)
