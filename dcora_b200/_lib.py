@@ -93,7 +93,7 @@ SYMBOLS = {
                                                 c_uint8_p, VP]),
     "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
     "dcora_problem_time_kernel": (C.c_int, [VP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
-    "dcora_debug_trsv_trace": (C.c_int, [VP, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
+    "dcora_debug_trsv_trace": (C.c_int, [VP, C.c_int32, c_uint8_p, C.POINTER(C.c_uint64), C.c_int32]),
     "dcora_selfcheck_layout": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, c_double_p]),
     "dcora_selfcheck_cholesky": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,

@@ -103,7 +103,13 @@ class _Arg:
         else:
             a = np.asarray(x, dtype=np.float64)
             assert a.shape == (r, K), f"expected shape {(r, K)}, got {a.shape}"
-            self.buf = np.asfortranarray(a) if not out else a
+            if out:
+                # the library writes column-major r x K doubles straight into this buffer
+                assert a is x and a.flags.f_contiguous and a.flags.writeable, \
+                    "output arrays must be float64, Fortran-ordered (column-major) and writeable"
+                self.buf = a
+            else:
+                self.buf = np.asfortranarray(a)
             self.ptr = self.buf.ctypes.data_as(C.c_void_p)
 
 

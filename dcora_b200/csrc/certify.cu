@@ -498,7 +498,14 @@ extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
   res->converged = converged;
   res->matvecs = matvecs;
   res->restarts = restarts;
-  res->is_psd = (lam + eta > 0.0) ? 1 : 0;
+  // Verdict.  `lam` is a Rayleigh quotient, i.e. an UPPER bound of lambda_min(S): a value
+  // below -eta proves "not PSD" whether or not the iteration converged, but "PSD" may only
+  // be claimed from a converged extreme Ritz pair whose residual leaves a margin (the
+  // reference decides with an exact Cholesky of S + eta I, DCORA_utils.cpp:1713-1747).
+  // Anything else is reported as not certified with converged = 0.
+  const bool proven_psd = converged && (lam - resid + eta > 0.0);
+  if (!proven_psd && lam + eta > 0.0) res->converged = 0;
+  res->is_psd = proven_psd ? 1 : 0;
   cleanup();
 #undef CERT_CUDA
   return DCORA_OK;

@@ -141,7 +141,13 @@ struct DeviceFactor {
   unsigned long long *tape = nullptr;  // all tapes, 8-byte words
   long long *tape_off = nullptr;       // A * nwarps: first word of each warp's tape
   int *tape_chunks = nullptr;          // A * nwarps: length in TAPE_CHUNK_WORDS chunks
-  int *nlev = nullptr;                 // A * 2: levels forward / backward
+  int *nslots = nullptr;               // A: barrier slots of every agent's tapes
+  long long *arow0 = nullptr;          // A + 1: first panel row of every agent
+  int *frow_col = nullptr;             // K: internal column of every factor row (global)
+  int max_slots = 0;
+  // cost model of the schedule (worst agent): busiest-warp iterations / rounds summed over
+  // the slots, and the perfectly balanced iteration count
+  int64_t crit_iters = 0, crit_rounds = 0, ideal_iters = 0;
   void release();
 };
 

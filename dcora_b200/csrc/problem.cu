@@ -103,6 +103,8 @@ int acquire_iterate(dcora_problem *p, const double *X, double *buf, double **out
     return DCORA_OK;
   }
   if (!buf) return DCORA_ERR_ALLOC;
+  // p->xe is about to hold something that is not the tracked buffer's content
+  if (buf == p->xe) p->tracked = nullptr;
   DCORA_TRY(import_matrix(p, X, buf, p->r));
   *out = buf;
   return DCORA_OK;
@@ -573,11 +575,12 @@ int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
   return DCORA_OK;
 }
 
-int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, int32_t all_agents,
+int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, const uint8_t *active,
                            uint64_t *stamps, int32_t max_stamps) {
   DCORA_ENTER(p);
   double *x = p->vec(WS_IO0), *t = p->vec(WS_IO1), *o = p->vec(WS_IO2);
-  if (!x || !t || !o || !stamps || max_stamps < 4) return DCORA_ERR_ARG;
+  if (!x || !t || !o || !stamps || max_stamps < 4 || agent < 0 || agent >= p->M->A)
+    return DCORA_ERR_ARG;
   if (!p->timing_ready) {
     double ms, by;
     DCORA_TRY(dcora_problem_time_kernel(p, DCORA_KERNEL_PROJECT, 1, &ms, &by));
@@ -586,8 +589,8 @@ int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, int32_t all_agents,
   DCORA_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * max_stamps));
   DCORA_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * max_stamps, p->stream));
   int mask = -1;
-  if (!all_agents) {
-    std::vector<uint8_t> act(p->M->A, 0);
+  if (active) {
+    std::vector<uint8_t> act(active, active + p->M->A);
     act[agent] = 1;
     DCORA_TRY(set_user_mask(p, act.data()));
     mask = F_USER;
@@ -597,7 +600,7 @@ int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, int32_t all_agents,
                              cudaMemcpyDeviceToHost, p->stream));
   DCORA_CUDA(cudaStreamSynchronize(p->stream));
   cudaFree(d);
-  if (!all_agents) DCORA_TRY(set_user_mask(p, nullptr));
+  if (active) DCORA_TRY(set_user_mask(p, nullptr));
   return DCORA_OK;
 }
 

@@ -99,6 +99,9 @@ int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
   DCORA_CUDA(upload(&C->rem_assign, H.rem_assign));
   DCORA_CUDA(upload(&C->rem_val, H.rem_val));
   p->C = C;
+  // launch lists cached per agent subset hold row lists of the previous coupling
+  p->act_cache.clear();
+  p->act.reset();
   cudaFree(p->xe); p->xe = nullptr; p->tracked = nullptr;
   cudaFree(p->hstage); p->hstage = nullptr;
   return DCORA_OK;

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -139,16 +141,18 @@ extern "C" int dcora_selfcheck_trsv(int32_t k, const int32_t *rowptr, const int3
   HostFactor F;
   DCORA_TRY(factor_for_check(k, rowptr, col, val, dh, npose, reg, ordering, &F));
   AgentTape S;
-  DCORA_TRY(build_agent_tape(F, dh, 48, 64, 0, &S));
+  const char *nwe = getenv("DCORA_SELFCHECK_WARPS");
+  const int nw = nwe ? atoi(nwe) : 48;
+  DCORA_TRY(build_agent_tape(F, dh, nw, std::max(nw, 64), 0, &S));
   if (factor_nnz) *factor_nnz = (int64_t)F.Lx.size();
   if (stored_values) *stored_values = S.stored_values / 2;
   if (nblocks) *nblocks = S.nblocks;
   if (levels_fwd) *levels_fwd = S.nlev[0];
   if (levels_bwd) *levels_bwd = S.nlev[1];
   uint64_t st = 7654321ull;
-  std::vector<double> b(k), x(k, 0.0), T(k + 8, 0.0), Y(k + 8, 0.0);
+  std::vector<double> b(k), x(k, 0.0), T(k + 8, 0.0), X(k + 8, 0.0);
   for (auto &v : b) v = prand(st);
-  agent_tape_apply_host(S, b.data(), x.data(), T.data(), Y.data());
+  agent_tape_apply_host(S, F, 0, b.data(), x.data(), T.data(), X.data());
   double rn = 0.0, bn = 0.0;
   for (int i = 0; i < k; ++i) {
     double s = reg * x[i];

@@ -19,6 +19,8 @@
 // (factor row, r) row-major, the same memory shape as every other vector.
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "kernels.cuh"
 #include "trsv.h"
 
@@ -27,7 +29,8 @@ namespace cg = cooperative_groups;
 namespace dcora {
 
 void DeviceFactor::release() {
-  cudaFree(tape); cudaFree(tape_off); cudaFree(tape_chunks); cudaFree(nlev);
+  cudaFree(tape); cudaFree(tape_off); cudaFree(tape_chunks); cudaFree(nslots);
+  cudaFree(arow0); cudaFree(frow_col);
   *this = DeviceFactor();
 }
 
@@ -40,7 +43,9 @@ constexpr int NCH = 4;                          // chunks per ring (8 KB per war
                                                 // iteration is ~1 KB, so 2 KB chunks halve the
                                                 // ring bookkeeping (arm + bulk copy) per iteration
 constexpr int RING_WORDS = NCH * CHW;
+constexpr int L2_AHEAD = 8;                     // chunks (16 KB) of L2 prefetch distance per warp
 constexpr int TRSV_SMEM = TRSV_NW * (RING_WORDS * 8 + NCH * 8);
+static_assert((RING_WORDS & (RING_WORDS - 1)) == 0, "ring size must be a power of two");
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -78,6 +83,12 @@ struct TapeReader {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         :: "r"(dst), "l"(g), "r"(CHW * 8), "r"(mb) : "memory");
+    // The ring holds 8 KB per warp: at an HBM round trip of > 1 us that alone would cap a
+    // warp's stream at a few GB/s.  The tape is static, so the chunk L2_AHEAD chunks further
+    // on is pulled into L2 now; by the time the ring asks for it, it is an L2 hit.
+    if (issued + L2_AHEAD < total)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                   :: "l"(g + (size_t)L2_AHEAD * CHW), "r"(CHW * 8) : "memory");
   }
   __device__ __forceinline__ void init(const unsigned long long *tape, int nchunks,
                                        unsigned long long *ring_, unsigned long long *mbar_,
@@ -92,8 +103,13 @@ struct TapeReader {
     }
     __syncwarp();
     const int n0 = total < NCH ? total : NCH;
-    if (lane == 0)
+    if (lane == 0) {
+      const int np = total < NCH + L2_AHEAD ? total : NCH + L2_AHEAD;
+      for (int c = NCH; c < np; ++c)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                     :: "l"(src + (size_t)c * CHW), "r"(CHW * 8) : "memory");
       for (; issued < n0; ++issued) issue_one();
+    }
     issued = n0;
   }
   // make words [.., upto) readable
@@ -111,18 +127,16 @@ struct TapeReader {
       ++ready;
     }
   }
-  // words below `pos` are consumed: recycle their chunks
+  // words below `pos` are consumed: recycle their chunk.  Callers advance by less
+  // than one chunk between calls, so at most one chunk is freed per call.
   __device__ __forceinline__ void release(int pos) {
-    const int done = pos / CHW;
-    if (freed < done) {
+    if (freed < pos / CHW) {
       __syncwarp();
-      while (freed < done) {
-        if (issued < total) {
-          if (lane == 0) issue_one();
-          ++issued;
-        }
-        ++freed;
+      if (issued < total) {
+        if (lane == 0) issue_one();
+        ++issued;
       }
+      ++freed;
     }
   }
   // wait for every copy still in flight (before the CTA may exit)
@@ -130,102 +144,112 @@ struct TapeReader {
   __device__ __forceinline__ unsigned long long word(int i) const {
     return ring[i & (RING_WORDS - 1)];
   }
-  __device__ __forceinline__ double dword(int i) const {
-    return __longlong_as_double((long long)ring[i & (RING_WORDS - 1)]);
-  }
 };
 
 __device__ __forceinline__ int lo32(unsigned long long u) { return (int)(unsigned)(u & 0xffffffffull); }
 __device__ __forceinline__ int hi32(unsigned long long u) { return (int)(unsigned)(u >> 32); }
 
-// Walks one direction of one agent's tape.  MODE 0: forward (right-hand side
-// gathered from V through the embedded permutation), MODE 1: backward (rhs =
-// forward solution in Y; the result overwrites Y in place and is scattered to
-// OUT through the permutation).
-template <int R, int DH, int CL, int MODE>
-__device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
-                                          const double *__restrict__ V, double *T,
-                                          double *Y, double *OUT,
-                                          unsigned long long *&trace, double *scratch) {
+// Executes every slot of one warp's tape (format: trsv.h).  Lane (g, a) of the
+// warp -- group g = lane / 4, a = lane % 4 -- owns COLUMN a of its group's
+// tile: per iteration it needs one row of the source panel (R doubles) and DH
+// tape words, and accumulates all DH rows of the product; the 4 lanes of a
+// group (and the `gpt` groups of a task) are summed once per round.
+template <int R, int DH, int CL>
+__device__ __forceinline__ void trsv_run(TapeReader &rd, int nslots, double *T, double *X,
+                                         unsigned long long *&trace) {
   constexpr int BS = DH * DH;
-  constexpr int ITW = 4 + 8 * BS;  // words per phase-A iteration
+  constexpr int ITW = 4 + 8 * BS;  // words per iteration
+  // The source rows are gathered from L2 PFD iterations ahead of their use
+  // (register ring, statically indexed by unrolling): 3 deep while the
+  // registers allow 2 CTAs per SM (r <= 8), 1 deep for higher ranks.
+  constexpr int PFD = R <= 8 ? 3 : 1;
   const int lane = rd.lane;
   const int g = lane >> 2, a = lane & 3;
-  for (int lv = 0; lv < nlev; ++lv) {
-    // ------------------------------------------------------------ phase A
-    rd.ensure(pos + 1);
-    const unsigned long long ah = rd.word(pos);
-    ++pos;
-    const int nrounds = lo32(ah);
+  const int cw_off = g >> 1;
+  const bool c_hi = (g & 1) != 0;
+  const int m_off = 4 + (g * DH + a) * DH;
+  int pos = 0;
+  for (int sl = 0; sl < nslots; ++sl) {
+    rd.ensure(pos + TAPE_SLOT_HEADER);
+    const int nrounds = lo32(rd.word(pos));
+    pos += TAPE_SLOT_HEADER;
     for (int rnd = 0; rnd < nrounds; ++rnd) {
-      rd.ensure(pos + 17);
+      rd.ensure(pos + TAPE_ROUND_HEADER);
       const unsigned long long rh = rd.word(pos);
-      const int niter = lo32(rh), gpt = hi32(rh);
-      const unsigned long long d0 = rd.word(pos + 1 + 2 * g), d1 = rd.word(pos + 2 + 2 * g);
-      const int r0 = lo32(d0), nrows = hi32(d0), pbase = lo32(d1);
-      pos = (pos + 17 + 3) & ~3;  // the iterations start 32-byte aligned on the tape
-      // lane (g, a) owns COLUMN a of its group's block: it needs one row of the
-      // source pose (R doubles of Y) per block and accumulates all DH rows of
-      // the product; the 4 lanes of a group are summed once per round.
+      const unsigned long long d0 = rd.word(pos + 1 + g);
+      const int niter = lo32(rh), gpt = hi32(rh) & 0xff, type = hi32(rh) >> 8;
+      const int r0 = lo32(d0), nrows = hi32(d0);
+      pos += TAPE_ROUND_HEADER;
+      const double *src = type == TAPE_BWD ? X : T;
+      double *dst = type == TAPE_FWD ? T : X;
+      const bool accumulate = type != TAPE_MID;
+      const bool writer = r0 >= 0 && a < nrows && (g & (gpt - 1)) == 0;
+      const size_t o = (size_t)(r0 + a) * R;
+      // the destination's current value (accumulating tasks): independent of
+      // everything below, so its latency hides behind the loop
+      double old[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) old[q] = 0.0;
+      if (accumulate && writer) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) old[q] = dst[o + q];
+      }
       double acc[4][R];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int q = 0; q < R; ++q) acc[i][q] = 0.0;
-      // The source rows of Y are gathered from L2 PFD iterations ahead of their use
-      // (register ring): 3 deep while the registers allow 2 CTAs per SM (r <= 8),
-      // 1 deep for higher ranks.  (Measured: 360 -> 352 us per solve; the phase is
-      // bound by the instruction stream of the tape walk, not by this latency.)
-      constexpr int PFD = R <= 8 ? 3 : 1;
       double yq[PFD][R];
 #pragma unroll
       for (int s2 = 0; s2 < PFD; ++s2)
 #pragma unroll
         for (int q = 0; q < R; ++q) yq[s2][q] = 0.0;
-      auto gather = [&](int ahead, double (&dst)[R]) {
-        rd.ensure(pos + (ahead + 1) * ITW);
-        const unsigned long long cw = rd.word(pos + ahead * ITW + (g >> 1));
-        const int c = (g & 1) ? hi32(cw) : lo32(cw);
+      const int base = pos;
+      auto gather = [&](int itn, double (&dstv)[R]) {
+        const int wpos = base + itn * ITW;
+        rd.ensure(wpos + 4);
+        const unsigned long long cw = rd.word(wpos + cw_off);
+        const int c = c_hi ? hi32(cw) : lo32(cw);
         if (a < DH) {
-          const double *yj = Y + (size_t)(c + a) * R;
+          const double *yj = src + (size_t)(c + a) * R;
 #pragma unroll
-          for (int q = 0; q < R; ++q) dst[q] = yj[q];
+          for (int q = 0; q < R; ++q) dstv[q] = yj[q];
         }
       };
 #pragma unroll
       for (int s2 = 0; s2 < PFD; ++s2)
-        if (niter > s2) gather(s2, yq[s2]);
-      for (int it = 0; it < niter; ++it) {
-        double yc[R], m[DH];
+        if (s2 < niter) gather(s2, yq[s2]);
+      for (int it0 = 0; it0 < niter; it0 += PFD) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          yc[q] = yq[0][q];
+        for (int u = 0; u < PFD; ++u) {
+          const int it = it0 + u;
+          if (it < niter) {
+            rd.ensure(pos + ITW);
+            double m[DH];
+            if (a < DH) {
+              const int mb = (pos + m_off) & (RING_WORDS - 1);
+              if constexpr (DH == 4) {
+                const double2 *mp = reinterpret_cast<const double2 *>(rd.ring + mb);
+                const double2 m01 = mp[0], m23 = mp[1];
+                m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
+              } else {
 #pragma unroll
-          for (int s2 = 0; s2 + 1 < PFD; ++s2) yq[s2][q] = yq[s2 + 1][q];
-        }
-        if (a < DH) {
-          // lane (g, a) owns DH consecutive tape words: column a of its block
-          const int base = pos + 4 + (g * DH + a) * DH;
-          if constexpr (DH == 4) {
-            const double2 *mp =
-                reinterpret_cast<const double2 *>(rd.ring + (base & (RING_WORDS - 1)));
-            const double2 m01 = mp[0], m23 = mp[1];
-            m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
-          } else {
+                for (int i = 0; i < DH; ++i)
+                  m[i] = __longlong_as_double((long long)rd.ring[(pos + m_off + i) & (RING_WORDS - 1)]);
+              }
+            } else {
 #pragma unroll
-            for (int i = 0; i < DH; ++i) m[i] = rd.dword(base + i);
+              for (int i = 0; i < DH; ++i) m[i] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < DH; ++i)
+#pragma unroll
+              for (int q = 0; q < R; ++q) acc[i][q] = fma(m[i], yq[u][q], acc[i][q]);
+            if (it + PFD < niter) gather(it + PFD, yq[u]);
+            pos += ITW;
+            rd.release(pos);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < DH; ++i) m[i] = 0.0;
         }
-        if (it + PFD < niter) gather(PFD, yq[PFD - 1]);
-#pragma unroll
-        for (int i = 0; i < DH; ++i)
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[i][q] = fma(m[i], yc[q], acc[i][q]);
-        pos += ITW;
-        rd.release(pos);
       }
       // sum over the 4 lanes of the group, leaving row a in lane a
       double row[R];
@@ -247,139 +271,38 @@ __device__ __forceinline__ void trsv_walk(TapeReader &rd, int &pos, int nlev,
           row[q] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
         }
       }
-      for (int o = 4; o < 4 * gpt; o <<= 1) {
+      for (int og = 4; og < 4 * gpt; og <<= 1) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) row[q] += __shfl_xor_sync(0xffffffffu, row[q], o);
+        for (int q = 0; q < R; ++q) row[q] += __shfl_xor_sync(0xffffffffu, row[q], og);
       }
-      if (r0 >= 0 && a < nrows && (g & (gpt - 1)) == 0) {
-        const size_t o = (size_t)(r0 + a) * R;
-        const double *rhs = MODE == 0 ? V + (size_t)(pbase + a) * R : Y + o;
+      if (writer) {
+        if (accumulate) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) T[o + q] = rhs[q] - row[q];
+          for (int q = 0; q < R; ++q) dst[o + q] = old[q] - row[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; ++q) dst[o + q] = row[q];
+        }
       }
       rd.release(pos);
-    }
-    if (hi32(ah) != 0) {  // the level has a phase A (agent-uniform)
-      phase_sync<CL>();
-      if (trace) *trace++ = globaltimer_ns() | 1ull;  // odd: end of a phase A
-    }
-    // ------------------------------------------------------------ phase B
-    rd.ensure(pos + 1);
-    const unsigned long long bh = rd.word(pos);
-    ++pos;
-    const int nsmall = lo32(bh), nlarge = hi32(bh);
-    // small blocks: lane = row, packed triangle consumed column by column
-    for (int s = 0; s < nsmall; ++s) {
-      rd.ensure(pos + 2);
-      const unsigned long long h0 = rd.word(pos), h1 = rd.word(pos + 1);
-      const int r0 = lo32(h0), w = hi32(h0);
-      const bool direct = MODE == 0 && lo32(h1) != 0;
-      pos += 2;
-      const int npw = (w + 1) >> 1;
-      rd.ensure(pos + npw);
-      int pm = 0;
-      if (lane < w) {
-        const unsigned long long pw = rd.word(pos + (lane >> 1));
-        pm = (lane & 1) ? hi32(pw) : lo32(pw);
-      }
-      pos += npw;
-      double tv[R], acc[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) { tv[q] = 0.0; acc[q] = 0.0; }
-      if (lane < w) {
-        const double *src = direct ? V + (size_t)pm * R : T + (size_t)(r0 + lane) * R;
-#pragma unroll
-        for (int q = 0; q < R; ++q) tv[q] = src[q];
-      }
-      // the block's right-hand side goes through this warp's shared scratch: row j is
-      // then a broadcast read (R shared loads) instead of 2 R shuffles per column
-      __syncwarp();
-      if (lane < w) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) scratch[lane * R + q] = tv[q];
-      }
-      __syncwarp();
-      rd.ensure(pos + w * (w + 1) / 2);  // the whole packed triangle (<= 528 words)
-      {
-        int off = pos;
-#pragma unroll 4
-        for (int j = 0; j < w; ++j) {
-          double m = 0.0;
-          if (MODE == 0) {            // column j holds rows j..w-1
-            if (lane >= j && lane < w) m = rd.dword(off + (lane - j));
-            off += w - j;
-          } else {                    // column j holds rows 0..j
-            if (lane <= j) m = rd.dword(off + lane);
-            off += j + 1;
-          }
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[q] = fma(m, scratch[j * R + q], acc[q]);
-        }
-        pos = off;
-      }
-      rd.release(pos);
-      if (lane < w) {
-        const size_t o = (size_t)(r0 + lane) * R;
-#pragma unroll
-        for (int q = 0; q < R; ++q) Y[o + q] = acc[q];
-        if (MODE == 1) {
-          const size_t oo = (size_t)pm * R;
-#pragma unroll
-          for (int q = 0; q < R; ++q) OUT[oo + q] = acc[q];
-        }
-      }
-    }
-    // rows of large blocks: lanes stride along the row
-    for (int l = 0; l < nlarge; ++l) {
-      rd.ensure(pos + 2);
-      const unsigned long long h0 = rd.word(pos), h1 = rd.word(pos + 1);
-      const int src0 = lo32(h0), len = hi32(h0);
-      const int dest = lo32(h1), dperm = hi32(h1);
-      pos += 2;
-      double acc[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) acc[q] = 0.0;
-      const double *srcp = T + (size_t)src0 * R;
-      for (int j0 = 0; j0 < len; j0 += CHW) {
-        const int n = len - j0 < CHW ? len - j0 : CHW;
-        rd.ensure(pos + n);
-#pragma unroll 4
-        for (int j = lane; j < n; j += 32) {
-          const double m = rd.dword(pos + j);
-          const double *sv = srcp + (size_t)(j0 + j) * R;
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[q] = fma(m, sv[q], acc[q]);
-        }
-        pos += n;
-        rd.release(pos);
-      }
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-      }
-      if (lane < R) {
-        double sres = 0.0;
-#pragma unroll
-        for (int q = 0; q < R; ++q)
-          if (q == lane) sres = acc[q];
-        Y[(size_t)dest * R + lane] = sres;
-        if (MODE == 1) OUT[(size_t)dperm * R + lane] = sres;
-      }
     }
     phase_sync<CL>();
-    if (trace) *trace++ = globaltimer_ns() & ~1ull;  // even: end of a phase B
+    if (trace) *trace++ = globaltimer_ns();
   }
+  // bring pos to the reader's notion for drain(): nothing to do
 }
 
+// One cluster per agent.  T <- permuted right-hand side, the slots of the
+// tape, then OUT <- solution X in internal column order.
 template <int R, int DH, int CL>
 __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
                  const int *__restrict__ agent_list,
                  const unsigned long long *__restrict__ tape,
                  const long long *__restrict__ tape_off, const int *__restrict__ tape_chunks,
-                 const int *__restrict__ nlev, const double *__restrict__ V, double *T,
-                 double *Y, double *OUT, unsigned long long *trace_buf, int trace_agent) {
+                 const int *__restrict__ nslots, const long long *__restrict__ arow0,
+                 const int *__restrict__ frow_col, const double *__restrict__ V, double *T,
+                 double *X, double *OUT, unsigned long long *trace_buf, int trace_agent) {
   const int slot = blockIdx.x / CL;
   const int agent = agent_list ? agent_list[slot] : slot;
   if (mask_flag >= 0 && flags[agent * NF + mask_flag] == 0) return;  // whole cluster
@@ -390,20 +313,32 @@ trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
   extern __shared__ __align__(128) unsigned long long trsv_smem[];
   unsigned long long *ring = trsv_smem + warp * RING_WORDS;
   unsigned long long *mbar = trsv_smem + TRSV_NW * RING_WORDS + warp * NCH;
-  double *scratch = reinterpret_cast<double *>(trsv_smem + TRSV_NW * (RING_WORDS + NCH)) +
-                    warp * (TRSV_SMALL_BLOCK * R);
   const size_t wi = (size_t)agent * nwarps + gwarp;
   TapeReader rd;
-  rd.init(tape + tape_off[wi], tape_chunks[wi], ring, mbar, lane);
+  rd.init(tape + tape_off[wi], tape_chunks[wi], ring, mbar, lane);  // the tape starts streaming
   // optional phase trace (debug / profiling aid): thread 0 of the traced
-  // agent's first CTA stamps the end of every phase
+  // agent's first CTA stamps the end of every slot
   unsigned long long *trace =
       (trace_buf && agent == trace_agent && gwarp == 0 && lane == 0) ? trace_buf : nullptr;
   if (trace) *trace++ = globaltimer_ns();
-  int pos = 0;
-  trsv_walk<R, DH, CL, 0>(rd, pos, nlev[agent * 2 + 0], V, T, Y, OUT, trace, scratch);
-  trsv_walk<R, DH, CL, 1>(rd, pos, nlev[agent * 2 + 1], V, T, Y, OUT, trace, scratch);
-  if (trace) *trace = 0ull;
+  // T[f] = V[column of factor row f]
+  const long long f0 = arow0[agent], f1 = arow0[agent + 1];
+  const int tid = crank * TRSV_THREADS + threadIdx.x;
+  constexpr int NT = CL * TRSV_THREADS;
+  for (long long e = (long long)f0 * R + tid; e < f1 * R; e += NT) {
+    const long long f = e / R;
+    const int q = (int)(e - f * R);
+    T[e] = V[(size_t)frow_col[f] * R + q];
+  }
+  phase_sync<CL>();
+  if (trace) *trace++ = globaltimer_ns();
+  trsv_run<R, DH, CL>(rd, nslots[agent], T, X, trace);
+  for (long long e = (long long)f0 * R + tid; e < f1 * R; e += NT) {
+    const long long f = e / R;
+    const int q = (int)(e - f * R);
+    OUT[(size_t)frow_col[f] * R + q] = X[e];
+  }
+  if (trace) { *trace++ = globaltimer_ns(); *trace = 0ull; }
   rd.drain();
 }
 
@@ -432,8 +367,9 @@ int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
   const int nwarps = cluster * TRSV_NW;
   int64_t nnzL = 0, stored = 0, words = 0;
   int max_levels = 0;
-  std::vector<long long> off((size_t)A * nwarps);
-  std::vector<int> chunks((size_t)A * nwarps), nlev((size_t)A * 2);
+  std::vector<long long> off((size_t)A * nwarps), arow0((size_t)A + 1);
+  std::vector<int> chunks((size_t)A * nwarps), nslots((size_t)A), frow_col((size_t)H.K);
+  F.crit_iters = F.ideal_iters = F.crit_rounds = 0;
   for (int a = 0; a < A; ++a) {
     nnzL += HF[a].nnz;
     stored += AT[a].stored_values;
@@ -446,10 +382,17 @@ int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
       chunks[(size_t)a * nwarps + w] = (int)(AT[a].warp_tape[w].size() / TAPE_CHUNK_WORDS);
       words += (int64_t)AT[a].warp_tape[w].size();
     }
-    nlev[a * 2 + 0] = AT[a].nlev[0];
-    nlev[a * 2 + 1] = AT[a].nlev[1];
+    nslots[a] = AT[a].nslots;
+    arow0[a] = H.coff[a];
+    const int k = (int)(H.coff[a + 1] - H.coff[a]);
+    for (int f = 0; f < k; ++f) frow_col[(size_t)H.coff[a] + f] = (int)H.coff[a] + HF[a].perm[f];
     max_levels = std::max(max_levels, std::max(AT[a].nlev[0], AT[a].nlev[1]));
+    F.crit_iters = std::max(F.crit_iters, AT[a].crit_iters);
+    F.crit_rounds = std::max(F.crit_rounds, AT[a].crit_rounds);
+    F.ideal_iters = std::max(F.ideal_iters, AT[a].ideal_iters);
+    F.max_slots = std::max(F.max_slots, AT[a].nslots);
   }
+  arow0[A] = H.coff[A];
   DCORA_CUDA(cudaMalloc(&F.tape, std::max<int64_t>(1, words) * sizeof(unsigned long long)));
   for (int a = 0; a < A; ++a) {
     for (int w = 0; w < nwarps; ++w) {
@@ -462,7 +405,9 @@ int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
   }
   DCORA_CUDA(up(&F.tape_off, off));
   DCORA_CUDA(up(&F.tape_chunks, chunks));
-  DCORA_CUDA(up(&F.nlev, nlev));
+  DCORA_CUDA(up(&F.nslots, nslots));
+  DCORA_CUDA(up(&F.arow0, arow0));
+  DCORA_CUDA(up(&F.frow_col, frow_col));
   F.present = true;
   F.nnzL = nnzL;
   F.stored_values = stored / 2;
@@ -473,8 +418,22 @@ int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
   return DCORA_OK;
 }
 
+// cudaFuncSetAttribute once per (instantiation, device); handles of different
+// devices may be driven from different host threads
 template <int R, int DH, int CL>
-static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
+static cudaError_t trsv_set_smem(int device, int smem_bytes) {
+  static std::mutex mtx;
+  static unsigned long long done = 0;  // bit d: set on device d
+  std::lock_guard<std::mutex> lock(mtx);
+  if (device < 64 && (done & (1ull << device))) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess && device < 64) done |= 1ull << device;
+  return e;
+}
+
+template <int R, int DH, int CL>
+static int launch_trsv(dcora_problem *p, const double *V, double *T, double *X,
                        double *OUT, int mask_flag, unsigned long long *trace,
                        int trace_agent) {
   DeviceMatrices &M = *p->M;
@@ -484,15 +443,10 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
   if (as && as->n_agents == 0) return DCORA_OK;
   cfg.gridDim = dim3((unsigned)((as ? as->n_agents : M.A) * CL));
   cfg.blockDim = dim3(TRSV_THREADS);
-  constexpr int smem_bytes = TRSV_SMEM + TRSV_NW * TRSV_SMALL_BLOCK * R * 8;  // + scratch
+  constexpr int smem_bytes = TRSV_SMEM;
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = p->stream;
-  static unsigned attr_done = 0;  // per instantiation: bit d = set on device d
-  if (M.device >= 32 || !(attr_done & (1u << M.device))) {
-    DCORA_CUDA(cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    if (M.device < 32) attr_done |= 1u << M.device;
-  }
+  DCORA_CUDA((trsv_set_smem<R, DH, CL>(M.device, smem_bytes)));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
@@ -504,7 +458,8 @@ static int launch_trsv(dcora_problem *p, const double *V, double *T, double *Y,
                                 mask_flag, (const int *)(as ? as->agents : nullptr),
                                 (const unsigned long long *)F.tape,
                                 (const long long *)F.tape_off, (const int *)F.tape_chunks,
-                                (const int *)F.nlev, V, T, Y, OUT, trace, trace_agent));
+                                (const int *)F.nslots, (const long long *)F.arow0,
+                                (const int *)F.frow_col, V, T, X, OUT, trace, trace_agent));
   p->launches++;
   return DCORA_OK;
 }

@@ -1,45 +1,69 @@
 // Block triangular-solve "tape" shared by trsv_host.cpp (construction, host
 // self check) and sptrsv.cu (upload + kernel).
 //
-// The schedule of one agent is compiled, at set-up, into one TAPE PER WARP of
-// the agent's thread-block cluster: the exact sequence of work items that warp
-// executes over all levels of the forward and the backward walk, with the
-// factor values it needs laid out in consumption order.  The kernel streams
-// each tape through a per-warp shared-memory ring with bulk asynchronous
-// copies (TMA), so every byte of the factor is read from HBM exactly once,
-// sequentially, and -- being static data -- arbitrarily far ahead of the level
-// barriers; only the gathers from the solution panel depend on a barrier.
+// The solve of one agent is compiled, at set-up, into one TAPE PER WARP of the
+// agent's thread-block cluster: the exact sequence of work items that warp
+// executes, with the factor values it needs laid out in consumption order.
+// The kernel streams each tape through a per-warp shared-memory ring with bulk
+// asynchronous copies (TMA), so every byte of the factor is read from HBM
+// exactly once, sequentially, and -- being static data -- arbitrarily far ahead
+// of the barriers; only the gathers from the solution panels depend on them.
+//
+// Everything is ONE kind of work item, a TILE TASK:
+//     dst[r0 .. r0+nrows) (-)= sum_t  M_t . src[c_t .. c_t+DH)
+// with DH x DH tiles M_t (DH = d+1; a pose is DH consecutive factor rows).  With the
+// factor regrouped by nested-dissection blocks B (diagonal block L_BB, D_B = inv(L_BB))
+// the solve  x = (L L^T)^-1 b  is rewritten so that ONE barrier per level of the block
+// elimination tree suffices in each direction:
+//     Lp[C, B] = L[C, B] D_B            (off-diagonal part with D folded in)
+//     G_B      = D_B^T D_B              (= inv(L_BB L_BB^T), dense symmetric)
+//   forward   T_C -= Lp[C, B] T_B       for the blocks B below C   (T starts as P b)
+//   mid       X_B  = G_B T_B            any time after T_B is final
+//   backward  X_B -= Lp[C, B]^T X_C     for the blocks C above B
+// (T_B = L_BB y_B of the textbook forward solve; D_B T_B never has to be formed on the
+// critical path.)  Three task types select the panels:
+//     TAPE_FWD: src T, dst T, accumulating     TAPE_MID: src T, dst X, assigning
+//     TAPE_BWD: src X, dst X, accumulating
+// Accumulating tasks may be cut into pieces that run in different barrier slots: a tile may
+// run in any slot after its SOURCE block is final (trsv_host.cpp uses that to take the long
+// rows of the top separators off the critical path and to keep the warps evenly loaded).
 //
 // A tape is a sequence of 8-byte words (doubles, or two packed int32):
-//   for dir in {forward, backward}: for level in 0..nlev[dir]-1:
-//     A header   {n_rounds, a_present}        a_present: the level has a phase A
+//   n_slots x slot:
+//     {n_rounds, 0} + 3 pad words
 //     n_rounds x round:
-//        {niter, gpt}
-//        8 x slot ( {row0 | -1, nrows}, {perm_base, 0} )   one slot per 4-lane group
-//        zero padding to a multiple of 4 words
-//        niter x ( 4 words: source rows c[0..7] ; 8 x DH x DH doubles: [group][b][a],
-//                  i.e. lane (group, b) owns DH consecutive words = column b of its block )
-//     B header   {n_small, n_large}
-//     n_small x  {row0, w} {direct, 0} ceil(w/2) words perm[] , w(w+1)/2 doubles
-//     n_large x  {src_row0, len} {dest_row, dest_perm} , len doubles
-// Phase A:  T[row0+a] = rhs[row0+a] - sum_blocks M[a][:] . Y[c .. c+DH)
-// Phase B:  Y[B] = D_B T[B]  (forward: packed lower, backward: D_B^T)
-// Rows are GLOBAL panel rows (agent offset included); perm entries are global
-// internal columns.
+//        {niter, gpt | type << 8}
+//        8 x { dst_row0 | -1, nrows }        one entry per 4-lane group
+//        3 pad words                         (iterations stay 32-byte aligned)
+//        niter x ( 4 words: source rows c[0..7] ;
+//                  8 x DH x DH doubles [group][b][a]: lane (group, b) owns DH
+//                  consecutive words = column b of its tile )
+//   a cluster barrier follows every slot.
+// `gpt` adjacent groups share one task (their partial sums are added at the
+// end of the round).  Rows are GLOBAL panel rows (agent offset included).
 #pragma once
 #include "common.cuh"
 
 namespace dcora {
 
-constexpr int TRSV_SMALL_BLOCK = 32;  // diagonal blocks of <= 32 rows: one warp, lane = row
 constexpr int TRSV_MAX_BLOCK = 512;   // larger ND blocks are split into a chain
 constexpr int TAPE_CHUNK_WORDS = 256; // 2 KB bulk-copy granularity of the tape ring
+constexpr int TAPE_SLOT_HEADER = 4;   // words of a slot header
+constexpr int TAPE_ROUND_HEADER = 12; // words before the first iteration of a round
+// (both multiples of 4: every iteration starts 32-byte aligned in the ring, so the
+//  128-bit loads of a lane's tile column never straddle the ring's end)
+
+enum TapeType : int { TAPE_FWD = 0, TAPE_MID = 1, TAPE_BWD = 2 };
 
 struct AgentTape {
   int k = 0, nblocks = 0, nwarps = 0, dh = 0;
+  int nslots = 0;
   int nlev[2] = {0, 0};
   std::vector<std::vector<uint64_t>> warp_tape;  // nwarps tapes, padded to whole chunks
   int64_t stored_values = 0;  // factor values on the tapes, both directions (incl. padding)
+  // cost model of the schedule: sum over slots of the busiest warp's
+  // iterations / rounds, and the perfectly balanced iteration count
+  int64_t crit_iters = 0, crit_rounds = 0, ideal_iters = 0;
 };
 
 // `row_offset`: global panel row of the agent's first factor row (== its
@@ -50,9 +74,9 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
                      AgentTape *out);
 
 // Sequential host replay of the tapes (same grouping and operand pairing as
-// the kernel): x = (L L^T)^-1 b with b, x in INTERNAL column order, global
-// indexing (only the agent's rows are touched).  R = 1.
-void agent_tape_apply_host(const AgentTape &S, const double *b, double *x,
-                           double *Tpanel, double *Ypanel);
+// the kernel): x = (L L^T)^-1 b with b, x in INTERNAL column order (agent
+// local).  R = 1.  T, X: scratch panels of >= k doubles.
+void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offset,
+                           const double *b, double *x, double *T, double *X);
 
 }  // namespace dcora

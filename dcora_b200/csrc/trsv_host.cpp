@@ -10,15 +10,26 @@
 //   forward   y_B = D_B ( b_B - L[B, <B] y )          D_B = inv(L[B, B])
 //   backward  x_B = D_B^T ( y_B - L[>B, B]^T x )
 //
-// so a block costs one sparse "phase A" (off-diagonal rows against the already
-// solved part, stored as dense (d+1)x(d+1) blocks) and one dense "phase B" (a
-// triangular matrix-vector product with the explicitly inverted diagonal
-// block); blocks of one level of the block elimination tree are independent
-// and the tree is only O(log n) levels deep.  The work of every phase is dealt
-// to the warps of the agent's cluster here, on the host, and written out as
-// one tape per warp (format: trsv.h).
+// Both the sparse part ("A": off-diagonal rows against the already solved
+// levels, (d+1)x(d+1) tiles) and the dense part ("B": the explicitly inverted
+// diagonal block, tiled the same way) are expressed as TILE TASKS (trsv.h) and
+// executed by one device loop.  Blocks of one level of the block elimination
+// tree are independent and the tree is O(log n) levels deep; a cluster barrier
+// separates the slots A(0) B(0) A(1) B(1) ...
+//
+// Scheduling.  An "A" task accumulates into its destination, so its tiles need
+// not run in the slot right before the destination's "B" task: a tile may run
+// in any slot after its SOURCE block is solved.  Long destination rows (the
+// top separators: hundreds of tiles per row, a handful of rows) are therefore
+// cut into pieces that run early, in the slots where their sources become
+// available; what remains on the critical path of an upper level is only the
+// contribution of the level just below it.  Inside a slot the tasks are packed
+// into rounds of 8 lane groups and dealt to the warps by longest-processing-
+// time; the cost model (AgentTape::crit_iters) is what DCORA_TAPE_STATS prints.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <queue>
@@ -73,16 +84,18 @@ void invert_diag_block(const HostFactor &F, int s, int e, std::vector<double> *D
   }
 }
 
-struct ATask {
-  int r0, nrows;
-  std::vector<int> src;        // source row starts, sorted
+struct Task {
+  int type = 0;                // TapeType
+  int r0 = 0, nrows = 0;       // destination rows (agent-local factor rows)
+  std::vector<int> src;        // source row starts (agent-local)
   std::vector<double> val;     // dh*dh per source, [a][b]
   int gpt = 1;
+  int ntiles() const { return (int)src.size(); }
 };
 
 struct Round {
-  int gpt, niter;
-  std::vector<int> tasks;      // indices into the level's task list (<= 8/gpt)
+  int type, gpt, niter;
+  std::vector<int> tasks;      // indices into the slot's task list (<= 8/gpt)
 };
 
 // longest-processing-time assignment: items sorted by decreasing cost
@@ -98,12 +111,23 @@ struct Lpt {
   }
 };
 
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+constexpr int ROUND_COST = 3;  // fixed cost of a round in units of one iteration
+
 }  // namespace
 
 int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, int row_offset,
                      AgentTape *out) {
   const int k = F.k;
   const int bs = dh * dh;
+  // long destination rows are cut into pieces of >= piece_min tiles that run as early as
+  // their sources allow; rows of <= split_min tiles stay whole
+  const int split_min = env_int("DCORA_TAPE_SPLIT", 24);
+  const int piece_min = std::max(1, env_int("DCORA_TAPE_PIECE", 12));
   // ---- final block partition: ND blocks, split to at most TRSV_MAX_BLOCK rows
   std::vector<int> bp(1, 0);
   for (size_t b = 0; b + 1 < F.blk_ptr.size(); ++b) {
@@ -161,6 +185,8 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
   out->dh = dh;
   out->warp_tape.assign(nwarps_total, std::vector<uint64_t>());
   out->stored_values = 0;
+  out->crit_iters = out->crit_rounds = out->ideal_iters = 0;
+  out->nslots = 0;
   const int R0 = row_offset;
   // first row of the (d+1)-row window a source column is read through: its pose
   // block, or -- for a unit-sphere / landmark row -- a window that stays inside
@@ -169,296 +195,372 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
     if (F.pose_start[c] >= 0) return F.pose_start[c];
     return std::max(0, std::min(c, k - dh));
   };
+  const bool stats = getenv("DCORA_TAPE_STATS") != nullptr;
 
+  // ---- levels of the block DAG, forward (L) and backward (L^T)
+  std::vector<int> lvl[2];
+  int nlev[2] = {0, 0};
   for (int dir = 0; dir < 2; ++dir) {
     const Csr &A = M[dir];
-    // levels of the block DAG
-    std::vector<int> lvl(nb, 0);
-    int nlev = 0;
+    lvl[dir].assign(nb, 0);
     for (int t = 0; t < nb; ++t) {
       const int b = dir == 0 ? t : nb - 1 - t;
       int lv = 0;
       for (int r = bp[b]; r < bp[b + 1]; ++r)
-        for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p) lv = std::max(lv, lvl[blk_of[A.col[p]]] + 1);
-      lvl[b] = lv;
-      nlev = std::max(nlev, lv + 1);
+        for (int p = A.ptr[r]; p < A.ptr[r + 1]; ++p)
+          lv = std::max(lv, lvl[dir][blk_of[A.col[p]]] + 1);
+      lvl[dir][b] = lv;
+      nlev[dir] = std::max(nlev[dir], lv + 1);
     }
-    out->nlev[dir] = nlev;
-    std::vector<std::vector<int>> by_level(nlev);
-    for (int b = 0; b < nb; ++b) by_level[lvl[b]].push_back(b);
+    out->nlev[dir] = nlev[dir];
+  }
+  const int Lf = nlev[0], Lb = nlev[1];
+  // global slots: forward level l (1..Lf-1) -> l - 1; the "mid" slot -> Lf - 1;
+  // backward level m (1..Lb-1) -> Lf - 1 + m
+  const int nslots_all = Lf + Lb - 1;
+  std::vector<std::vector<Task>> slots((size_t)std::max(1, nslots_all));
+  std::vector<int64_t> slot_load(slots.size(), 0);
 
-    for (int lv = 0; lv < nlev; ++lv) {
-      // ------------------------------------------------ phase A tasks
-      std::vector<ATask> tasks;
-      std::vector<int> direct_of(by_level[lv].size(), 0);
-      int64_t total_blocks = 0;
-      for (size_t bi = 0; bi < by_level[lv].size(); ++bi) {
-        const int b = by_level[lv][bi];
-        const int s = bp[b], e = bp[b + 1];
-        bool has = false;
-        for (int r = s; r < e && !has; ++r) has = A.ptr[r + 1] > A.ptr[r];
-        // only small forward blocks without predecessors read their right-hand
-        // side directly (through perm); everything else gets a phase-A task
-        const int direct = (dir == 0 && !has && e - s <= TRSV_SMALL_BLOCK) ? 1 : 0;
-        direct_of[bi] = direct;
-        if (direct) continue;
-        for (int r = s; r < e;) {
-          ATask tk;
-          tk.r0 = r;
-          tk.nrows = F.pose_start[r] == r ? dh : 1;
-          // sources: pose blocks (start row ps) or single scalar rows (b = 0)
+  // ---- folded off-diagonal rows  Lp[i, B] = L[i, B] D_B  (dense from the block's first
+  // column to the row's last non-zero column in B)
+  struct RowPart { int blk, len; std::vector<double> v; };
+  std::vector<std::vector<RowPart>> lp(k);
+  std::vector<std::vector<std::pair<int, int>>> rows_of_block(nb);  // (row, index in lp[row])
+  for (int i = 0; i < k; ++i) {
+    const Csr &A = M[0];
+    for (int p = A.ptr[i]; p < A.ptr[i + 1];) {
+      const int b = blk_of[A.col[p]];
+      int q = p;
+      while (q < A.ptr[i + 1] && blk_of[A.col[q]] == b) ++q;
+      const int s = bp[b], w = bp[b + 1] - s;
+      const std::vector<double> &D = Dinv[b];
+      RowPart rp;
+      rp.blk = b;
+      rp.len = A.col[q - 1] - s + 1;
+      rp.v.assign(rp.len, 0.0);
+      for (int t = p; t < q; ++t) {
+        const int c = A.col[t] - s;
+        const double lv = A.val[t];
+        const double *dr = &D[(size_t)c * w];
+        for (int j = 0; j <= c; ++j) rp.v[j] += lv * dr[j];
+      }
+      rows_of_block[b].push_back(std::make_pair(i, (int)lp[i].size()));
+      lp[i].push_back(std::move(rp));
+      p = q;
+    }
+  }
+
+  // A destination's tiles, each with the first slot it may run in, become one task in the
+  // destination's own (last) slot -- or, for long rows, several pieces that run as early as
+  // their sources allow.
+  auto emit_pieces = [&](int type, int r0, int nrows, const std::vector<int> &src,
+                         const std::vector<double> &val, const std::vector<int> &avail,
+                         int last) {
+    std::vector<int> ord(src.size());
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return avail[x] < avail[y]; });
+    auto emit = [&](size_t i0, size_t i1, int slot) {
+      Task tk;
+      tk.type = type; tk.r0 = r0; tk.nrows = nrows;
+      for (size_t i = i0; i < i1; ++i) {
+        tk.src.push_back(src[ord[i]]);
+        tk.val.insert(tk.val.end(), val.begin() + (size_t)ord[i] * bs,
+                      val.begin() + (size_t)(ord[i] + 1) * bs);
+      }
+      slot_load[slot] += tk.ntiles();
+      slots[slot].push_back(std::move(tk));
+    };
+    if ((int)src.size() <= split_min) { emit(0, src.size(), last); return; }
+    size_t i0 = 0;
+    for (size_t i = 0; i < ord.size();) {
+      size_t j = i;
+      while (j < ord.size() && avail[ord[j]] == avail[ord[i]]) ++j;
+      const int slot = avail[ord[i]];
+      if (slot < last && (int)(j - i0) >= piece_min) { emit(i0, j, slot); i0 = j; }
+      i = j;
+    }
+    if (i0 < ord.size()) emit(i0, ord.size(), last);
+  };
+
+  // ---- forward tasks:  T[C rows] -= Lp[C rows, B] T[B]
+  for (int r = 0; r < k;) {
+    const int nrows = F.pose_start[r] == r ? dh : 1;
+    const int lc = lvl[0][blk_of[r]];
+    // blocks touched by the group's rows, with the longest row part
+    std::vector<std::pair<int, int>> bl;  // (block, len)
+    for (int a = 0; a < nrows; ++a)
+      for (const RowPart &rp : lp[r + a]) bl.push_back(std::make_pair(rp.blk, rp.len));
+    std::sort(bl.begin(), bl.end());
+    std::vector<int> src, avail;
+    std::vector<double> val;
+    for (size_t i = 0; i < bl.size(); ++i) {
+      if (i + 1 < bl.size() && bl[i + 1].first == bl[i].first) continue;  // keep the longest
+      const int b = bl[i].first, len = bl[i].second, s = bp[b];
+      for (int j = 0; j * dh < len; ++j) {
+        const int c = s + j * dh;
+        const int ps = std::max(0, std::min(c, k - dh));
+        std::vector<double> tv((size_t)bs, 0.0);
+        for (int a = 0; a < nrows; ++a)
+          for (const RowPart &rp : lp[r + a]) {
+            if (rp.blk != b) continue;
+            for (int jj = j * dh; jj < std::min(rp.len, (j + 1) * dh); ++jj)
+              tv[(size_t)a * dh + (s + jj - ps)] = rp.v[jj];
+          }
+        src.push_back(ps);
+        val.insert(val.end(), tv.begin(), tv.end());
+        avail.push_back(lvl[0][b]);
+      }
+    }
+    if (!src.empty()) emit_pieces(TAPE_FWD, r, nrows, src, val, avail, lc - 1);
+    r += nrows;
+  }
+
+  // ---- backward tasks:  X[B tile] -= Lp[C rows, B tile]^T X[C rows]
+  for (int b = 0; b < nb; ++b) {
+    const int s = bp[b], w = bp[b + 1] - s;
+    const int nt = (w + dh - 1) / dh;
+    const std::vector<std::pair<int, int>> &rows = rows_of_block[b];  // ascending rows
+    for (int t = 0; t < nt; ++t) {
+      const int nrows = std::min(dh, w - t * dh);
+      std::vector<int> src, avail;
+      std::vector<double> val;
+      int cur_ps = -1;
+      for (const std::pair<int, int> &ri : rows) {
+        const int i = ri.first;
+        const RowPart &rp = lp[i][ri.second];
+        if (rp.len <= t * dh) continue;
+        const int ps = src_start(i);
+        if (ps != cur_ps) {
+          src.push_back(ps);
+          val.insert(val.end(), (size_t)bs, 0.0);
+          avail.push_back(0);
+          cur_ps = ps;
+        }
+        double *tv = &val[val.size() - bs];
+        for (int a = 0; a < nrows; ++a) {
+          const int jj = t * dh + a;
+          if (jj < rp.len) tv[(size_t)a * dh + (i - ps)] = rp.v[jj];
+        }
+        avail.back() = std::max(avail.back(), Lf + lvl[1][blk_of[i]]);
+      }
+      if (!src.empty())
+        emit_pieces(TAPE_BWD, s + t * dh, nrows, src, val, avail, Lf - 1 + lvl[1][b]);
+    }
+  }
+
+  // ---- "mid" tasks:  X[B] = G_B T[B],  G_B = D_B^T D_B = (L_BB L_BB^T)^-1.  T[B] is final
+  // after the block's forward slot and X[B] is first needed by the backward slots: the
+  // task goes to the least loaded slot in between.
+  {
+    std::vector<int> border(nb);
+    std::iota(border.begin(), border.end(), 0);
+    std::stable_sort(border.begin(), border.end(), [&](int x, int y) {
+      if (lvl[0][x] != lvl[0][y]) return lvl[0][x] > lvl[0][y];  // tightest windows first
+      return bp[x + 1] - bp[x] > bp[y + 1] - bp[y];
+    });
+    for (int b : border) {
+      const int s = bp[b], w = bp[b + 1] - s;
+      const int nt = (w + dh - 1) / dh;
+      const std::vector<double> &D = Dinv[b];
+      std::vector<double> G((size_t)w * w, 0.0);
+      for (int i = 0; i < w; ++i)
+        for (int j = 0; j <= i; ++j) {
+          double acc = 0.0;
+          for (int kk = i; kk < w; ++kk) acc += D[(size_t)kk * w + i] * D[(size_t)kk * w + j];
+          G[(size_t)i * w + j] = acc;
+          G[(size_t)j * w + i] = acc;
+        }
+      int slot = lvl[0][b];
+      for (int c = lvl[0][b]; c <= Lf - 1; ++c)
+        if (slot_load[c] < slot_load[slot]) slot = c;
+      for (int i = 0; i < nt; ++i) {
+        Task tk;
+        tk.type = TAPE_MID;
+        tk.r0 = s + i * dh;
+        tk.nrows = std::min(dh, w - i * dh);
+        for (int j = 0; j < nt; ++j) {
+          const int c = s + j * dh;
+          const int ps = std::max(0, std::min(c, k - dh));
+          std::vector<double> tv((size_t)bs, 0.0);
           for (int a = 0; a < tk.nrows; ++a)
-            for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
-              tk.src.push_back(src_start(A.col[p]));
-            }
-          std::sort(tk.src.begin(), tk.src.end());
-          tk.src.erase(std::unique(tk.src.begin(), tk.src.end()), tk.src.end());
-          tk.val.assign(tk.src.size() * (size_t)bs, 0.0);
-          for (int a = 0; a < tk.nrows; ++a)
-            for (int p = A.ptr[r + a]; p < A.ptr[r + a + 1]; ++p) {
-              const int c = A.col[p];
-              const int ps = src_start(c);
-              const size_t q = std::lower_bound(tk.src.begin(), tk.src.end(), ps) - tk.src.begin();
-              tk.val[q * bs + (size_t)a * dh + (c - ps)] = A.val[p];
-            }
-          total_blocks += (int64_t)tk.src.size();
-          r += tk.nrows;
-          tasks.push_back(std::move(tk));
+            for (int jj = j * dh; jj < std::min(w, (j + 1) * dh); ++jj)
+              tv[(size_t)a * dh + (s + jj - ps)] = G[(size_t)(i * dh + a) * w + jj];
+          tk.src.push_back(ps);
+          tk.val.insert(tk.val.end(), tv.begin(), tv.end());
         }
-      }
-      const bool a_present = !tasks.empty();
-      // groups per task: split tasks that are long compared with the ideal
-      // per-group load of the level
-      const int64_t target = std::max<int64_t>(2, (total_blocks + (int64_t)nwarps * 8 - 1) / ((int64_t)nwarps * 8));
-      for (ATask &tk : tasks) {
-        int g = 1;
-        while (g < 8 && (int64_t)tk.src.size() > target * g) g *= 2;
-        tk.gpt = g;
-      }
-      std::vector<int> ord(tasks.size());
-      std::iota(ord.begin(), ord.end(), 0);
-      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
-        if (tasks[x].gpt != tasks[y].gpt) return tasks[x].gpt > tasks[y].gpt;
-        return tasks[x].src.size() > tasks[y].src.size();
-      });
-      std::vector<Round> rounds;
-      for (size_t i = 0; i < ord.size();) {
-        Round rd;
-        rd.gpt = tasks[ord[i]].gpt;
-        rd.niter = 0;
-        const int tpw = 8 / rd.gpt;
-        while (i < ord.size() && (int)rd.tasks.size() < tpw && tasks[ord[i]].gpt == rd.gpt) {
-          const int nbk = (int)tasks[ord[i]].src.size();
-          rd.niter = std::max(rd.niter, (nbk + rd.gpt - 1) / rd.gpt);
-          rd.tasks.push_back(ord[i]);
-          ++i;
-        }
-        rounds.push_back(std::move(rd));
-      }
-      std::stable_sort(rounds.begin(), rounds.end(),
-                       [](const Round &x, const Round &y) { return x.niter > y.niter; });
-      std::vector<std::vector<int>> warp_rounds(nwarps);
-      {
-        Lpt lpt(nwarps);
-        for (size_t i = 0; i < rounds.size(); ++i)
-          warp_rounds[lpt.take(rounds[i].niter + 2)].push_back((int)i);
-      }
-      // ------------------------------------------------ phase B items
-      struct Small { int b, direct; };
-      struct Large { int b, i, len; };
-      std::vector<Small> smalls;
-      std::vector<Large> larges;
-      for (size_t bi = 0; bi < by_level[lv].size(); ++bi) {
-        const int b = by_level[lv][bi];
-        const int w = bp[b + 1] - bp[b];
-        if (w <= TRSV_SMALL_BLOCK) smalls.push_back({b, direct_of[bi]});
-        else for (int i = 0; i < w; ++i) larges.push_back({b, i, dir == 0 ? i + 1 : w - i});
-      }
-      std::stable_sort(smalls.begin(), smalls.end(), [&](const Small &x, const Small &y) {
-        return bp[x.b + 1] - bp[x.b] > bp[y.b + 1] - bp[y.b];
-      });
-      std::stable_sort(larges.begin(), larges.end(),
-                       [](const Large &x, const Large &y) { return x.len > y.len; });
-      std::vector<std::vector<int>> warp_small(nwarps), warp_large(nwarps);
-      {
-        Lpt lpt(nwarps);
-        for (size_t i = 0; i < smalls.size(); ++i)
-          warp_small[lpt.take(bp[smalls[i].b + 1] - bp[smalls[i].b] + 16)].push_back((int)i);
-        for (size_t i = 0; i < larges.size(); ++i)
-          warp_large[lpt.take(larges[i].len / 16 + 8)].push_back((int)i);
-      }
-      // ------------------------------------------------ emit
-      for (int wi = 0; wi < nwarps; ++wi) {
-        std::vector<uint64_t> &tp = out->warp_tape[wi];
-        tp.push_back(pack2((int)warp_rounds[wi].size(), a_present ? 1 : 0));
-        for (int ri : warp_rounds[wi]) {
-          const Round &rd = rounds[ri];
-          tp.push_back(pack2(rd.niter, rd.gpt));
-          for (int g = 0; g < 8; ++g) {
-            const int ti = g / rd.gpt;
-            if (ti < (int)rd.tasks.size()) {
-              const ATask &tk = tasks[rd.tasks[ti]];
-              tp.push_back(pack2(R0 + tk.r0, tk.nrows));
-              tp.push_back(pack2(R0 + F.perm[tk.r0], 0));
-            } else {
-              tp.push_back(pack2(-1, 0));
-              tp.push_back(pack2(0, 0));
-            }
-          }
-          while (tp.size() % 4) tp.push_back(0);  // iterations start 32-byte aligned
-          for (int it = 0; it < rd.niter; ++it) {
-            int c[8];
-            const double *vp[8];
-            for (int g = 0; g < 8; ++g) {
-              const int ti = g / rd.gpt, gg = g % rd.gpt;
-              c[g] = R0;  // padding: any valid row, zero block
-              vp[g] = nullptr;
-              if (ti < (int)rd.tasks.size()) {
-                const ATask &tk = tasks[rd.tasks[ti]];
-                const int q = it * rd.gpt + gg;
-                if (q < (int)tk.src.size()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
-              }
-            }
-            for (int g = 0; g < 8; g += 2) tp.push_back(pack2(c[g], c[g + 1]));
-            // lane (group g, column bb) owns DH consecutive words: its column of the
-            // block, rows 0..DH-1 (one address computation and, for DH = 4, two
-            // 128-bit shared loads per iteration on the device)
-            for (int g = 0; g < 8; ++g)
-              for (int bb = 0; bb < dh; ++bb)
-                for (int a = 0; a < dh; ++a)
-                  tp.push_back(dbits(vp[g] ? vp[g][a * dh + bb] : 0.0));
-            out->stored_values += 8 * bs;
-          }
-        }
-        tp.push_back(pack2((int)warp_small[wi].size(), (int)warp_large[wi].size()));
-        for (int si : warp_small[wi]) {
-          const int b = smalls[si].b, s = bp[b], w = bp[b + 1] - s;
-          const std::vector<double> &D = Dinv[b];
-          tp.push_back(pack2(R0 + s, w));
-          tp.push_back(pack2(smalls[si].direct, 0));
-          for (int i = 0; i < w; i += 2)
-            tp.push_back(pack2(R0 + F.perm[s + i], i + 1 < w ? R0 + F.perm[s + i + 1] : 0));
-          // packed by columns: forward lower (column j: rows j..w-1 of D),
-          // backward upper (column j: rows 0..j of D^T, i.e. D[j][0..j])
-          for (int j = 0; j < w; ++j) {
-            if (dir == 0) for (int i = j; i < w; ++i) tp.push_back(dbits(D[(size_t)i * w + j]));
-            else for (int i = 0; i <= j; ++i) tp.push_back(dbits(D[(size_t)j * w + i]));
-          }
-          out->stored_values += (int64_t)w * (w + 1) / 2;
-        }
-        for (int li : warp_large[wi]) {
-          const Large &lg = larges[li];
-          const int s = bp[lg.b], w = bp[lg.b + 1] - s, i = lg.i;
-          const std::vector<double> &D = Dinv[lg.b];
-          const int j0 = dir == 0 ? 0 : i;
-          tp.push_back(pack2(R0 + s + j0, lg.len));
-          tp.push_back(pack2(R0 + s + i, R0 + F.perm[s + i]));
-          // forward row i = D[i][0..i]; backward row i of D^T = D[i..w-1][i]
-          if (dir == 0) for (int j = 0; j <= i; ++j) tp.push_back(dbits(D[(size_t)i * w + j]));
-          else for (int j = i; j < w; ++j) tp.push_back(dbits(D[(size_t)j * w + i]));
-          out->stored_values += lg.len;
-        }
-      }
-      // warps of a larger launch cluster than this agent's own (batches mix
-      // agent sizes; the work split of an agent depends on the agent alone, so
-      // its result does not depend on what it is batched with): barriers only
-      for (int wi = nwarps; wi < nwarps_total; ++wi) {
-        out->warp_tape[wi].push_back(pack2(0, a_present ? 1 : 0));
-        out->warp_tape[wi].push_back(pack2(0, 0));
+        slot_load[slot] += tk.ntiles();
+        slots[slot].push_back(std::move(tk));
       }
     }
   }
+
+  // ---------------------------------------------------- pack every slot and emit
+  for (size_t sl = 0; sl < slots.size(); ++sl) {
+    std::vector<Task> &tasks = slots[sl];
+    out->nslots++;   // (an empty slot still costs its barrier: there is none in practice)
+    int64_t total = 0;
+    for (const Task &tk : tasks) total += tk.ntiles();
+    // groups per task: split tasks that are long compared with the ideal
+    // per-group load of the slot
+    const int64_t target =
+        std::max<int64_t>(2, (total + (int64_t)nwarps * 8 - 1) / ((int64_t)nwarps * 8));
+    for (Task &tk : tasks) {
+      int g = 1;
+      while (g < 8 && (int64_t)tk.ntiles() > target * g) g *= 2;
+      tk.gpt = g;
+    }
+    std::vector<int> ord(tasks.size());
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+      if (tasks[x].type != tasks[y].type) return tasks[x].type < tasks[y].type;
+      if (tasks[x].gpt != tasks[y].gpt) return tasks[x].gpt > tasks[y].gpt;
+      return tasks[x].ntiles() > tasks[y].ntiles();
+    });
+    std::vector<Round> rounds;
+    for (size_t i = 0; i < ord.size();) {
+      Round rd;
+      rd.type = tasks[ord[i]].type;
+      rd.gpt = tasks[ord[i]].gpt;
+      rd.niter = 0;
+      const int tpw = 8 / rd.gpt;
+      while (i < ord.size() && (int)rd.tasks.size() < tpw && tasks[ord[i]].gpt == rd.gpt &&
+             tasks[ord[i]].type == rd.type) {
+        const int nbk = tasks[ord[i]].ntiles();
+        rd.niter = std::max(rd.niter, (nbk + rd.gpt - 1) / rd.gpt);
+        rd.tasks.push_back(ord[i]);
+        ++i;
+      }
+      rounds.push_back(std::move(rd));
+    }
+    std::stable_sort(rounds.begin(), rounds.end(),
+                     [](const Round &x, const Round &y) { return x.niter > y.niter; });
+    std::vector<std::vector<int>> warp_rounds(nwarps);
+    {
+      Lpt lpt(nwarps);
+      for (size_t i = 0; i < rounds.size(); ++i)
+        warp_rounds[lpt.take(rounds[i].niter + ROUND_COST)].push_back((int)i);
+    }
+    {
+      int maxit = 0, maxrounds = 0, maxtask = 0;
+      for (int wi = 0; wi < nwarps; ++wi) {
+        int it = 0;
+        for (int ri : warp_rounds[wi]) it += rounds[ri].niter;
+        maxit = std::max(maxit, it);
+        maxrounds = std::max(maxrounds, (int)warp_rounds[wi].size());
+      }
+      for (const Task &tk : tasks) maxtask = std::max(maxtask, tk.ntiles());
+      const int64_t ideal = (total + (int64_t)nwarps * 8 - 1) / ((int64_t)nwarps * 8);
+      out->crit_iters += maxit;
+      out->crit_rounds += maxrounds;
+      out->ideal_iters += ideal;
+      if (stats)
+        fprintf(stderr, "[tape] slot %2zu (%s): tasks %5zu tiles %7lld maxtask %4d rounds %4zu | "
+                        "busiest warp: %3d iterations %2d rounds (ideal %lld)\n",
+                sl, (int)sl < Lf - 1 ? "fwd" : (int)sl == Lf - 1 ? "mid" : "bwd", tasks.size(),
+                (long long)total, maxtask, rounds.size(), maxit, maxrounds, (long long)ideal);
+    }
+    for (int wi = 0; wi < nwarps; ++wi) {
+      std::vector<uint64_t> &tp = out->warp_tape[wi];
+      tp.push_back(pack2((int)warp_rounds[wi].size(), 0));
+      for (int z = 1; z < TAPE_SLOT_HEADER; ++z) tp.push_back(0);
+      for (int ri : warp_rounds[wi]) {
+        const Round &rd = rounds[ri];
+        tp.push_back(pack2(rd.niter, rd.gpt | (rd.type << 8)));
+        for (int g = 0; g < 8; ++g) {
+          const int ti = g / rd.gpt;
+          if (ti < (int)rd.tasks.size()) {
+            const Task &tk = tasks[rd.tasks[ti]];
+            tp.push_back(pack2(R0 + tk.r0, tk.nrows));
+          } else {
+            tp.push_back(pack2(-1, 0));
+          }
+        }
+        for (int z = 9; z < TAPE_ROUND_HEADER; ++z) tp.push_back(0);
+        for (int it = 0; it < rd.niter; ++it) {
+          int c[8];
+          const double *vp[8];
+          for (int g = 0; g < 8; ++g) {
+            const int ti = g / rd.gpt, gg = g % rd.gpt;
+            c[g] = R0;  // padding: any valid row, zero tile
+            vp[g] = nullptr;
+            if (ti < (int)rd.tasks.size()) {
+              const Task &tk = tasks[rd.tasks[ti]];
+              const int q = it * rd.gpt + gg;
+              if (q < tk.ntiles()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
+            }
+          }
+          for (int g = 0; g < 8; g += 2) tp.push_back(pack2(c[g], c[g + 1]));
+          // lane (group g, column bb) owns DH consecutive words: its column of the
+          // tile, rows 0..DH-1 (for DH = 4: two 128-bit shared loads per iteration)
+          for (int g = 0; g < 8; ++g)
+            for (int bb = 0; bb < dh; ++bb)
+              for (int a = 0; a < dh; ++a)
+                tp.push_back(dbits(vp[g] ? vp[g][a * dh + bb] : 0.0));
+          out->stored_values += 8 * bs;
+        }
+      }
+    }
+    // warps of a larger launch cluster than this agent's own (batches mix
+    // agent sizes; the work split of an agent depends on the agent alone, so
+    // its result does not depend on what it is batched with): barriers only
+    for (int wi = nwarps; wi < nwarps_total; ++wi)
+      for (int z = 0; z < TAPE_SLOT_HEADER; ++z) out->warp_tape[wi].push_back(0);
+  }
+  if (stats)
+    fprintf(stderr, "[tape] k %d blocks %d levels %d/%d slots %d: busiest-warp iterations %lld "
+                    "(ideal %lld), rounds %lld, stored values %lld (2 nnz(L) = %lld)\n",
+            k, nb, Lf, Lb, out->nslots, (long long)out->crit_iters, (long long)out->ideal_iters,
+            (long long)out->crit_rounds, (long long)out->stored_values,
+            2 * (long long)F.Lx.size());
   for (std::vector<uint64_t> &tp : out->warp_tape)
     while (tp.size() % TAPE_CHUNK_WORDS) tp.push_back(0);
   return DCORA_OK;
 }
 
-// CPU replay of the tapes, warp by warp within a phase (phases are separated
-// by barriers on the device).
-void agent_tape_apply_host(const AgentTape &S, const double *b, double *x, double *T,
-                           double *Y) {
-  const int dh = S.dh, bs = dh * dh, nw = S.nwarps;
+// CPU replay of the tapes, slot by slot (slots are separated by barriers on the
+// device; inside a slot no task reads what another one writes).
+void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offset,
+                           const double *b, double *x, double *T, double *X) {
+  const int dh = S.dh, bs = dh * dh, nw = S.nwarps, R0 = row_offset;
+  for (int f = 0; f < S.k; ++f) T[R0 + f] = b[F.perm[f]];
   std::vector<size_t> pos(nw, 0);
-  struct Write { int row; double v; };
-  for (int dir = 0; dir < 2; ++dir) {
-    for (int lv = 0; lv < S.nlev[dir]; ++lv) {
-      // phase A
-      for (int wi = 0; wi < nw; ++wi) {
-        const std::vector<uint64_t> &tp = S.warp_tape[wi];
-        size_t &p = pos[wi];
-        const int nrounds = lo32(tp[p]);
-        ++p;
-        for (int rd = 0; rd < nrounds; ++rd) {
-          const int niter = lo32(tp[p]), gpt = hi32(tp[p]);
-          ++p;
-          int r0[8], nrows[8], pb[8];
-          for (int g = 0; g < 8; ++g) {
-            r0[g] = lo32(tp[p]); nrows[g] = hi32(tp[p]); pb[g] = lo32(tp[p + 1]);
-            p += 2;
-          }
-          std::vector<double> acc(8 * 4, 0.0);
-          p = (p + 3) & ~(size_t)3;
-          for (int it = 0; it < niter; ++it) {
-            int c[8];
-            for (int g = 0; g < 8; g += 2) { c[g] = lo32(tp[p]); c[g + 1] = hi32(tp[p]); ++p; }
-            for (int g = 0; g < 8; ++g)
-              for (int a = 0; a < dh; ++a)
-                for (int bb = 0; bb < dh; ++bb)
-                  acc[g * 4 + a] += bitsd(tp[p + (size_t)(g * dh + bb) * dh + a]) * Y[c[g] + bb];
-            p += 8 * bs;
-          }
-          for (int g = 0; g < 8; g += gpt) {
-            if (r0[g] < 0) continue;
-            for (int a = 0; a < nrows[g]; ++a) {
-              double s = 0.0;
-              for (int gg = 0; gg < gpt; ++gg) s += acc[(g + gg) * 4 + a];
-              const double rhs = dir == 0 ? b[pb[g] + a] : Y[r0[g] + a];
-              T[r0[g] + a] = rhs - s;
-            }
+  for (int sl = 0; sl < S.nslots; ++sl) {
+    for (int wi = 0; wi < nw; ++wi) {
+      const std::vector<uint64_t> &tp = S.warp_tape[wi];
+      size_t &p = pos[wi];
+      const int nrounds = lo32(tp[p]);
+      p += TAPE_SLOT_HEADER;
+      for (int rd = 0; rd < nrounds; ++rd) {
+        const int niter = lo32(tp[p]);
+        const int gpt = hi32(tp[p]) & 0xff, type = hi32(tp[p]) >> 8;
+        int r0[8], nrows[8];
+        for (int g = 0; g < 8; ++g) { r0[g] = lo32(tp[p + 1 + g]); nrows[g] = hi32(tp[p + 1 + g]); }
+        p += TAPE_ROUND_HEADER;
+        const double *src = type == TAPE_BWD ? X : T;
+        double *dst = type == TAPE_FWD ? T : X;
+        const bool accumulate = type != TAPE_MID;
+        std::vector<double> acc(8 * 4, 0.0);
+        for (int it = 0; it < niter; ++it) {
+          int c[8];
+          for (int g = 0; g < 8; g += 2) { c[g] = lo32(tp[p]); c[g + 1] = hi32(tp[p]); ++p; }
+          for (int g = 0; g < 8; ++g)
+            for (int a = 0; a < dh; ++a)
+              for (int bb = 0; bb < dh; ++bb)
+                acc[g * 4 + a] += bitsd(tp[p + (size_t)(g * dh + bb) * dh + a]) * src[c[g] + bb];
+          p += 8 * bs;
+        }
+        for (int g = 0; g < 8; g += gpt) {
+          if (r0[g] < 0) continue;
+          for (int a = 0; a < nrows[g]; ++a) {
+            double s = 0.0;
+            for (int gg = 0; gg < gpt; ++gg) s += acc[(g + gg) * 4 + a];
+            dst[r0[g] + a] = accumulate ? dst[r0[g] + a] - s : s;
           }
         }
       }
-      // phase B (writes applied after every warp has read: the device barrier)
-      std::vector<Write> writes;
-      for (int wi = 0; wi < nw; ++wi) {
-        const std::vector<uint64_t> &tp = S.warp_tape[wi];
-        size_t &p = pos[wi];
-        const int nsmall = lo32(tp[p]), nlarge = hi32(tp[p]);
-        ++p;
-        for (int s = 0; s < nsmall; ++s) {
-          const int r0 = lo32(tp[p]), w = hi32(tp[p]);
-          const int direct = lo32(tp[p + 1]);
-          p += 2;
-          std::vector<int> pm(w);
-          for (int i = 0; i < w; i += 2) {
-            pm[i] = lo32(tp[p]);
-            if (i + 1 < w) pm[i + 1] = hi32(tp[p]);
-            ++p;
-          }
-          std::vector<double> tv(w), acc(w, 0.0);
-          for (int i = 0; i < w; ++i) tv[i] = direct ? b[pm[i]] : T[r0 + i];
-          for (int j = 0; j < w; ++j) {
-            if (dir == 0) for (int i = j; i < w; ++i) acc[i] += bitsd(tp[p++]) * tv[j];
-            else for (int i = 0; i <= j; ++i) acc[i] += bitsd(tp[p++]) * tv[j];
-          }
-          for (int i = 0; i < w; ++i) {
-            writes.push_back({r0 + i, acc[i]});
-            if (dir == 1) x[pm[i]] = acc[i];
-          }
-        }
-        for (int l = 0; l < nlarge; ++l) {
-          const int src0 = lo32(tp[p]), len = hi32(tp[p]);
-          const int dest = lo32(tp[p + 1]), dperm = hi32(tp[p + 1]);
-          p += 2;
-          double acc = 0.0;
-          for (int j = 0; j < len; ++j) acc += bitsd(tp[p++]) * T[src0 + j];
-          writes.push_back({dest, acc});
-          if (dir == 1) x[dperm] = acc;
-        }
-      }
-      for (const Write &wv : writes) Y[wv.row] = wv.v;
     }
   }
+  for (int f = 0; f < S.k; ++f) x[F.perm[f]] = X[R0 + f];
 }
 
 }  // namespace dcora

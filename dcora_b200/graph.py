@@ -111,6 +111,7 @@ class GlobalProblem:
     """Column bookkeeping + global data matrix of a partitioned problem."""
 
     def __init__(self, meas: Measurements, part: Partition, ra: bool | None = None):
+        meas = drop_duplicate_edges(meas)
         self.meas, self.part = meas, part
         d = self.d = meas.d
         self.ra = meas.range_aided if ra is None else ra
@@ -317,6 +318,36 @@ class GlobalProblem:
         for p in pairs:
             adj[p // self.A].add(int(p % self.A))
         return adj
+
+
+def drop_duplicate_edges(meas: Measurements) -> Measurements:
+    """Graph keeps the FIRST measurement of every EdgeID (src, dst) and silently drops
+    later duplicates (src/Graph.cpp:139-141,162-169; duplicate ranges are fatal there,
+    :174-181).  Returns `meas` itself when there is nothing to drop."""
+    import dataclasses
+
+    def first_of(i, j):
+        if len(i) == 0:
+            return None
+        key = np.stack([i, j], 1)
+        _, first = np.unique(key, axis=0, return_index=True)
+        return None if len(first) == len(i) else np.sort(first)
+
+    kp = first_of(meas.pp_i, meas.pp_j)
+    kl = first_of(meas.pl_i, meas.pl_j)
+    if len(meas.rg_i):
+        kr = first_of(meas.rg_i, meas.rg_j)
+        assert kr is None, "range measurements must be unique (Graph.cpp:174-181)"
+    if kp is None and kl is None:
+        return meas
+    kw = {f.name: getattr(meas, f.name) for f in dataclasses.fields(meas)}
+    if kp is not None:
+        for nm in ("pp_i", "pp_j", "pp_R", "pp_t", "pp_kappa", "pp_tau", "pp_w"):
+            kw[nm] = kw[nm][kp]
+    if kl is not None:
+        for nm in ("pl_i", "pl_j", "pl_t", "pl_tau", "pl_w"):
+            kw[nm] = kw[nm][kl]
+    return Measurements(**kw)
 
 
 def greedy_coloring(adj):

@@ -222,11 +222,12 @@ class RBCD:
         return self.X.cpu().numpy().T.copy()
 
     # -- exchange (Agent::getSharedStateDicts -> updateNeighborStates) ----------
-    def exchange(self):
+    def exchange(self, src=None):
+        """All-gather of the public columns of `src` (default: the iterate X)."""
         if self.world == 1:
             return
         import torch.distributed as dist
-        self.P.pack_columns(self.X, self.plan.pack_idx, out=self.sendbuf)
+        self.P.pack_columns(self.X if src is None else src, self.plan.pack_idx, out=self.sendbuf)
         dist.all_gather_into_tensor(self.H, self.sendbuf, group=self.group)
         self.torch.cuda.current_stream().synchronize()
 
@@ -234,44 +235,59 @@ class RBCD:
     def iterate(self):
         for c in range(self.plan.num_colors):
             active = (self.local_colors == c).astype(np.uint8)
-            if self.acc:
-                self._accelerated_step(active)
-                continue
-            self.exchange()
-            if active.any():
-                self.P.update_G(self.X, self.H, active)
-                self.X = self.opt.optimize(self.X, active, out=self.X)
-                self.agent_updates += int(active.sum())
+            self.step(active)
+
+    def step(self, active):
+        """One driver iteration (examples/MultiRobotExample.cpp:223-258): the agents in
+        `active` (local mask; they must share no measurement) take Agent::iterate(true),
+        all others iterate(false)."""
+        active = np.ascontiguousarray(active, dtype=np.uint8)
+        if self.acc:
+            self._accelerated_step(active)
+            return
+        self.exchange()
+        if active.any():
+            self.P.update_G(self.X, self.H, active)
+            self.X = self.opt.optimize(self.X, active, out=self.X)
+            self.agent_updates += int(active.sum())
 
     def _accelerated_step(self, active):
-        """One driver iteration of RBCD++: the agents in `active` run
-        Agent::iterate(true), all others iterate(false) (Agent.cpp:535-596).  The
-        drivers hand X (not Y) to the selected agent as auxiliary neighbour states
-        (MultiRobotExample.cpp:247-258), so G is built from the previous iterate."""
+        """One driver iteration of RBCD++ (Agent.cpp:535-596).  The non-selected agents run
+        iterate(false) FIRST -- X <- Y, or X <- XPrev on a restart iteration (:1165-1176) --
+        and only then does the selected agent fetch its neighbours' public states
+        (MultiRobotExample.cpp:228-258), so its G is built from the neighbours' NEW X: their Y
+        on an ordinary iteration, their XPrev on a restart iteration (every agent shares the
+        iteration counter, so all restart together).  On a restart iteration the selected
+        agent's first solve (from Y) is overwritten by restartNesterovAcceleration's solve
+        from XPrev, so only that one is run here."""
         N = self.gp.A
         self.it += 1
-        self.exchange()                                   # public columns of XPrev = X
-        Xprev = self.X.clone()
+        Xprev = self.X
         self.gamma = (1 + np.sqrt(1 + 4 * N ** 2 * self.gamma ** 2)) / (2 * N)   # updateGamma
         self.alpha = 1 / (self.gamma * N)                                       # updateAlpha
+        restart = (self.it + 1) % self.restart_interval == 0                    # shouldRestart
+        if restart:
+            Xr = Xprev.clone()
+            self.exchange(Xprev)
+            if active.any():
+                self.P.update_G(Xprev, self.H, active)
+                Xr = self.opt.optimize(Xprev, active, out=Xr)
+                self.agent_updates += int(active.sum())
+            self.X, self.V, self.Y = Xr, Xr.clone(), Xr.clone()
+            self.gamma = 0.0
+            self.alpha = 0.0
+            return
         # updateY: Y = projectToManifold((1 - alpha) X + alpha V), every agent
         Y = self.P.combine_project(1 - self.alpha, self.X, self.alpha, self.V, None)
         Xn = Y.clone()                                    # iterate(false): X = Y
+        self.exchange(Y)
         if active.any():
-            self.P.update_G(Xprev, self.H, active)
+            self.P.update_G(Y, self.H, active)
             Xn = self.opt.optimize(Y, active, out=Xn)
             self.agent_updates += int(active.sum())
         # updateV: V = projectToManifold(V + gamma (X - Y))
         V = self.P.combine_project(1.0, self.V, self.gamma, Xn - Y, None)
         self.X, self.V, self.Y = Xn, V, Y
-        if (self.it + 1) % self.restart_interval == 0:    # shouldRestart / restartNesterov...
-            Xr = Xprev.clone()
-            if active.any():
-                self.P.update_G(Xprev, self.H, active)
-                Xr = self.opt.optimize(Xprev, active, out=Xr)
-            self.X, self.V, self.Y = Xr, Xr.clone(), Xr.clone()
-            self.gamma = 0.0
-            self.alpha = 0.0
 
     def monitor(self):
         """Global cost f and Riemannian gradient norm (the centralised

@@ -290,12 +290,13 @@ int dcora_problem_time_spmm(dcora_problem *p, int32_t iters, double *ms_mean,
 int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
                               double *ms_mean, double *algorithmic_bytes);
 
-/* Profiling aid: runs the preconditioner kernel (K5) with a phase trace for one
+/* Profiling aid: runs the preconditioner kernel (K5) with a slot trace for one
  * agent and returns the %globaltimer stamps (ns) of its first CTA: stamps[0] =
- * start, then one stamp per finished phase (odd = sparse phase A, even = dense
- * phase B), forward levels first, terminated by 0.  all_agents != 0 keeps every
- * agent of the batch active (loaded machine), 0 runs the traced agent alone. */
-int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, int32_t all_agents,
+ * start, stamps[1] = right-hand side loaded, then one stamp per finished barrier
+ * slot (forward slots first), one after the write-back, terminated by 0.
+ * `active` (num_agents bytes, NULL: every agent) selects the agents that run
+ * concurrently with the traced one (which is always active). */
+int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, const uint8_t *active,
                            uint64_t *stamps, int32_t max_stamps);
 
 /* Host-only self checks of the setup code (no GPU needed, no usable result):

@@ -78,36 +78,44 @@ class RBCD:
                 Xn[:, b.c0:b.c1] = self._optimize(a, self.X[:, b.c0:b.c1], self.X)
             self.X = Xn
             return
-        # RBCD++ (Agent.cpp:544-554).  The drivers send X (not Y) as the
-        # auxiliary neighbour states (MultiRobotExample.cpp:247-258).
+        # RBCD++ (Agent.cpp:544-554).  The driver runs iterate(false) on every
+        # non-selected agent BEFORE the selected agent fetches its neighbours'
+        # public states (MultiRobotExample.cpp:228-258): the neighbour states that
+        # enter G are the neighbours' new X, i.e. their Y -- or, on a restart
+        # iteration (all agents share the counter), their XPrev (:1165-1176).
         N = self.A
         Xprev = self.X.copy()
         self.gamma = (1 + np.sqrt(1 + 4 * N ** 2 * self.gamma ** 2)) / (2 * N)
         self.alpha = 1 / (self.gamma * N)
+        restart = (self.it + 1) % self.restart_interval == 0   # shouldRestart (:1158-1163)
         Y = np.empty_like(self.X)
         for b in self.blocks:
             s = slice(b.c0, b.c1)
             Y[:, s] = mf.project_manifold(b.L, (1 - self.alpha) * self.X[:, s]
                                           + self.alpha * self.V[:, s])
-        Xn = Y.copy()                                   # iterate(false): X = Y
+        # state of every agent after iterate(false)
+        Xfalse = Xprev if restart else Y
+        Xn = Xfalse.copy()
         for a in sel:
             b = self.blocks[a]
-            Xn[:, b.c0:b.c1] = self._optimize(a, Y[:, b.c0:b.c1], Xprev)
+            if restart:
+                # updateX(true, true) from Y, then restartNesterovAcceleration:
+                # X = XPrev; updateX(true, false) -- the second solve is the one kept
+                Xn[:, b.c0:b.c1] = self._optimize(a, Xprev[:, b.c0:b.c1], Xfalse)
+            else:
+                Xn[:, b.c0:b.c1] = self._optimize(a, Y[:, b.c0:b.c1], Xfalse)
+        if restart:
+            self.X = Xn
+            self.V = Xn.copy()
+            self.Y = Xn.copy()
+            self.gamma = 0.0
+            self.alpha = 0.0
+            return
         V = np.empty_like(self.X)
         for b in self.blocks:
             s = slice(b.c0, b.c1)
             V[:, s] = mf.project_manifold(b.L, self.V[:, s] + self.gamma * (Xn[:, s] - Y[:, s]))
         self.X, self.V, self.Y = Xn, V, Y
-        if (self.it + 1) % self.restart_interval == 0:  # shouldRestart (:1158-1163)
-            Xr = Xprev.copy()
-            for a in sel:                               # updateX(doOptimization, false)
-                b = self.blocks[a]
-                Xr[:, b.c0:b.c1] = self._optimize(a, Xprev[:, b.c0:b.c1], Xprev)
-            self.X = Xr
-            self.V = Xr.copy()
-            self.Y = Xr.copy()
-            self.gamma = 0.0
-            self.alpha = 0.0
 
     def sweep(self, colors):
         """One iteration per colour."""

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Phase trace of the preconditioner kernel (K5) on the bench workload: prints
-the duration of every phase A / phase B of one agent's forward and backward
-walk, alone on the GPU and with every agent of the batch active.
+"""Slot trace of the preconditioner kernel (K5) on the bench workload: prints the
+duration of every barrier slot of one agent's solve -- alone on the GPU, with the
+agents of its colour class active (what an RBCD colour step runs), and with the
+whole batch active.
 
     python tools/trsv_trace.py [--grid 100 --agents 256 --agent 128]
 """
@@ -30,19 +31,21 @@ def main():
     gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, a.agents))
     S = rbcd.RBCD(gp, a.rank, rank=0, world=1, device=0, params=dc.ROptParameters(time_bound_s=0.0))
     n = 256
-    for all_agents in (0, 1):
+    alone = np.zeros(a.agents, np.uint8)
+    colour = (S.local_colors == S.local_colors[a.agent]).astype(np.uint8)
+    for name, act in (("alone", alone), (f"its colour class ({int(colour.sum())} agents)", colour),
+                      ("whole batch", None)):
         st = (C.c_uint64 * n)()
-        _lib.check(lib.dcora_debug_trsv_trace(S.P.h, a.agent, all_agents, st, n))
+        ptr = act.ctypes.data_as(_lib.c_uint8_p) if act is not None else None
+        _lib.check(lib.dcora_debug_trsv_trace(S.P.h, a.agent, ptr, st, n))
         t = np.array(list(st), dtype=np.uint64)
         end = int(np.argmax(t[1:] == 0)) + 1
         t = t[:end].astype(np.int64)
-        kinds = ["A" if (x & 1) else "B" for x in t[1:]]
         dt = np.diff(t) / 1e3
-        print(f"--- agent {a.agent}, {'all agents active' if all_agents else 'alone'}: "
-              f"total {(t[-1] - t[0]) / 1e3:.1f} us over {len(dt)} phases")
-        print("  A total %.1f us, B total %.1f us" % (
-            sum(d for d, k in zip(dt, kinds) if k == "A"), sum(d for d, k in zip(dt, kinds) if k == "B")))
-        print("  " + " ".join(f"{k}{d:.1f}" for d, k in zip(dt, kinds)))
+        print(f"--- agent {a.agent}, {name}: total {(t[-1] - t[0]) / 1e3:.1f} us, "
+              f"{len(dt) - 2} slots")
+        print(f"  rhs load {dt[0]:.1f} | slots " + " ".join(f"{d:.1f}" for d in dt[1:-1]) +
+              f" | write-back {dt[-1]:.1f}")
 
 
 if __name__ == "__main__":
