@@ -13,7 +13,9 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdcora_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["layout.cpp", "chol.cpp", "trsv_host.cpp", "selfcheck.cpp", "kernels.cu", "sptrsv.cu", "problem.cu",
-           "solver.cu", "certify.cu", "rbcd.cu"]
+           "solver.cu", "rtr_cluster.cu", "certify.cu", "rbcd.cu"]
+# (source, extra flags, object tag): the per-agent RTR cluster kernel, one translation unit per rank
+VARIANTS = [("rtr_cluster_inst.cu", [f"-DDCORA_CLUSTER_R={r}"], f"r{r}") for r in range(2, 9)]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
          "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr", "-diag-suppress", "128"]
 
@@ -30,13 +32,14 @@ def _deps_hash(src):
     return h.hexdigest()
 
 
-def _compile(src):
-    obj = os.path.join(BUILD, src + ".o")
+def _compile(job):
+    src, extra, tag = job if isinstance(job, tuple) else (job, [], "")
+    obj = os.path.join(BUILD, src + (("." + tag) if tag else "") + ".o")
     stamp = obj + ".sha1"
-    want = _deps_hash(src)
+    want = _deps_hash(src) + "".join(extra)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
         return obj, False
-    cmd = [NVCC, *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC, *FLAGS, *extra, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
     subprocess.run(cmd, check=True)
     with open(stamp, "w") as fh:
         fh.write(want)
@@ -46,7 +49,8 @@ def _compile(src):
 def build(verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+    srcs = [v for v in VARIANTS if os.path.exists(os.path.join(CSRC, v[0]))] + srcs   # slowest first
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(srcs))) as ex:
         results = list(ex.map(_compile, srcs))
     objs = [o for o, _ in results]
     if any(ch for _, ch in results) or not os.path.exists(LIB):

@@ -136,14 +136,15 @@ struct DeviceFactor {
   int64_t stored_values = 0;  // factor values one direction of the tapes stores
   int64_t tape_bytes = 0;     // both directions, with headers and padding
   int A = 0;
-  int cluster = 1;            // CTAs per agent
+  int nwarps = 8;             // warps per agent (8, 16, 32 or 64): cluster shape at launch
   int max_levels = 0;
   unsigned long long *tape = nullptr;  // all tapes, 8-byte words
   long long *tape_off = nullptr;       // A * nwarps: first word of each warp's tape
-  int *tape_chunks = nullptr;          // A * nwarps: length in TAPE_CHUNK_WORDS chunks
+  int *tape_chunks = nullptr;          // A * nwarps: length in records
   int *nslots = nullptr;               // A: barrier slots of every agent's tapes
   long long *arow0 = nullptr;          // A + 1: first panel row of every agent
   int *frow_col = nullptr;             // K: internal column of every factor row (global)
+  int *col_frow = nullptr;             // K: factor row of every internal column (global)
   int max_slots = 0;
   // cost model of the schedule (worst agent): busiest-warp iterations / rounds summed over
   // the slots, and the perfectly balanced iteration count
@@ -185,6 +186,8 @@ struct DeviceMatrices {
   double *rem_val = nullptr;
   Chunk *chunks = nullptr;
   int *agent_chunk0 = nullptr;
+  int *chunk_pose0 = nullptr;   // nchunks: first pose block row of a pose chunk (-1 otherwise)
+  int2 *chunk_rem = nullptr;    // nchunks: [first, end) remainder rows with their row in the chunk
   DeviceFactor F;
   ~DeviceMatrices();
 };

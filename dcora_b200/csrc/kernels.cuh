@@ -92,9 +92,8 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
                    const double *dot_with = nullptr);
 struct AgentTape;
 int upload_factor(dcora::DeviceMatrices *M, const std::vector<HostFactor> &F,
-                  std::vector<AgentTape> &tapes, int cluster, const HostLayout &H);
-int trsv_cluster_for(double rows_per_agent);  // CTAs per agent
-int trsv_warps_per_cta();
+                  std::vector<AgentTape> &tapes, int nwarps, const HostLayout &H);
+int trsv_warps_for(double rows_per_agent);  // warps one agent's solve is dealt to
 
 // workspace vector indices (p->vec(i))
 enum Ws : int {

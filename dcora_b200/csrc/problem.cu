@@ -25,6 +25,7 @@ DeviceMatrices::~DeviceMatrices() {
   cudaFree(pose_agent); cudaFree(rem_agent); cudaFree(bval);
   cudaFree(rem_row); cudaFree(rem_rowptr); cudaFree(rem_col);
   cudaFree(rem_assign); cudaFree(rem_val); cudaFree(chunks); cudaFree(agent_chunk0);
+  cudaFree(chunk_pose0); cudaFree(chunk_rem);
   F.release();
 }
 
@@ -245,6 +246,23 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
   DCORA_CUDA(upload(&M->rem_assign, H.rem_assign));
   DCORA_CUDA(upload(&M->chunks, H.chunks));
   DCORA_CUDA(upload(&M->agent_chunk0, H.agent_chunk0));
+  {
+    // per chunk: its pose block rows and its remainder rows (both are sorted by column)
+    std::vector<int> pose0(H.chunks.size(), -1);
+    std::vector<int2> remr(H.chunks.size());
+    size_t s = 0;
+    for (size_t c = 0; c < H.chunks.size(); ++c) {
+      const Chunk &ch = H.chunks[c];
+      if (ch.kind == KIND_POSE)
+        pose0[c] = H.poff[ch.agent] + (ch.col0 - (int)H.coff[ch.agent]) / (d + 1);
+      while (s < H.rem_row.size() && H.rem_row[s] < ch.col0) ++s;
+      remr[c].x = (int)s;
+      while (s < H.rem_row.size() && H.rem_row[s] < ch.col0 + ch.ncols) ++s;
+      remr[c].y = (int)s;
+    }
+    DCORA_CUDA(upload(&M->chunk_pose0, pose0));
+    DCORA_CUDA(upload(&M->chunk_rem, remr));
+  }
 
   // ---- preconditioner factors (host) -> device
   bool any = false;
@@ -256,10 +274,9 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
     std::vector<AgentTape> AT(num_agents);
     // launch cluster = the largest agent's; every agent's own split depends
     // only on its size
-    int cluster = 1;
+    int tape_warps = 8;
     for (int a = 0; a < num_agents; ++a)
-      cluster = std::max(cluster, trsv_cluster_for((double)(H.coff[a + 1] - H.coff[a])));
-    const int tape_warps = cluster * trsv_warps_per_cta();
+      tape_warps = std::max(tape_warps, trsv_warps_for((double)(H.coff[a + 1] - H.coff[a])));
     std::vector<int> rcs(num_agents, DCORA_OK);
     const int dh = d + 1;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -301,8 +318,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       // input).
       rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a]);
       if (rcs[a] == DCORA_OK) {
-        rcs[a] = build_agent_tape(HF[a], dh, trsv_cluster_for((double)k) * trsv_warps_per_cta(),
-                                  tape_warps, c0, &AT[a]);
+        rcs[a] = build_agent_tape(HF[a], dh, trsv_warps_for((double)k), tape_warps, c0, &AT[a]);
         // only nnz(L) and the permutation are needed from here on
         const size_t nnz = HF[a].Lx.size();
         std::vector<int>().swap(HF[a].Li);
@@ -316,7 +332,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
         set_error("Cholesky factorisation of Q + reg*I failed for agent " + std::to_string(a));
         return DCORA_ERR_FACTOR;
       }
-    DCORA_TRY(upload_factor(M.get(), HF, AT, cluster, H));
+    DCORA_TRY(upload_factor(M.get(), HF, AT, tape_warps, H));
   }
 
   dcora_problem *p = new dcora_problem();

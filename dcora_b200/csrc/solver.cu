@@ -576,7 +576,9 @@ extern "C" int dcora_rtr_solve(dcora_problem *p, const double *X0, double *Xopt,
     if (!x1) return DCORA_ERR_ALLOC;
     DCORA_TRY(import_matrix(p, X0, x1, p->r));
   }
-  const int rc_solve = rtr_solve_device(p, x1, &prm, active, results);
+  const int rc_solve = rtr_cluster_applicable(p, &prm)
+                           ? rtr_solve_cluster(p, x1, &prm, active, results)
+                           : rtr_solve_device(p, x1, &prm, active, results);
   if (track) p->tracked = nullptr;   // xe changed; re-established by the write-back below
   if (rc_solve < 0) return rc_solve;
   if (in_place_tracked) {

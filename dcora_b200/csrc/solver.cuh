@@ -25,4 +25,13 @@ int eval_f(dcora_problem *p, const double *X, double *tmp, int slot, int mask_fl
 // flags[a][F_USER] <- active[a] (NULL: all agents)
 int set_user_mask(dcora_problem *p, const uint8_t *active);
 
+// RTR / tCG of the selected agents (x1: internal layout, updated in place):
+// per-operation launches over the whole GPU (solver.cu) ...
+int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
+                     const uint8_t *active, dcora_ropt_result *results);
+// ... or one launch, one cluster per agent (rtr_cluster.cu)
+int rtr_solve_cluster(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
+                      const uint8_t *active, dcora_ropt_result *results);
+bool rtr_cluster_applicable(const dcora_problem *p, const dcora_ropt_params *prm);
+
 }  // namespace dcora

@@ -28,30 +28,28 @@
 // run in any slot after its SOURCE block is final (trsv_host.cpp uses that to take the long
 // rows of the top separators off the critical path and to keep the warps evenly loaded).
 //
-// A tape is a sequence of 8-byte words (doubles, or two packed int32):
-//   n_slots x slot:
-//     {n_rounds, 0} + 3 pad words
-//     n_rounds x round:
-//        {niter, gpt | type << 8}
-//        8 x { dst_row0 | -1, nrows }        one entry per 4-lane group
-//        3 pad words                         (iterations stay 32-byte aligned)
-//        niter x ( 4 words: source rows c[0..7] ;
-//                  8 x DH x DH doubles [group][b][a]: lane (group, b) owns DH
-//                  consecutive words = column b of its tile )
-//   a cluster barrier follows every slot.
-// `gpt` adjacent groups share one task (their partial sums are added at the
-// end of the round).  Rows are GLOBAL panel rows (agent offset included).
+// A tape is a sequence of fixed-size RECORDS of 16 + 8 DH^2 8-byte words (doubles, or two
+// packed int32), one record per iteration of a round; the kernel moves one record per bulk
+// copy (TMA) into one slot of the warp's shared-memory ring:
+//   word 0..3    source rows c[0..7] of the 8 lane groups (two int32 per word)
+//   word 4       {niter, gpt | type << 8 | last_of_slot << 16}   (first record of a round)
+//   word 5..12   8 x { dst_row0 | -1, nrows }, one per lane group (first record of a round)
+//   word 13..15  padding
+//   word 16..    8 x DH x DH doubles [group][b][a]: lane (group, b) owns DH consecutive
+//                words = column b of its tile
+// A round = `niter` records executed by one warp: `gpt` adjacent groups share one task
+// (their partial sums are added at the end of the round).  A cluster barrier follows the
+// round flagged last_of_slot; every warp of the agent has exactly one such round per slot
+// (a zero record when it has no work there).  Rows are GLOBAL panel rows (agent offset
+// included).
 #pragma once
 #include "common.cuh"
 
 namespace dcora {
 
 constexpr int TRSV_MAX_BLOCK = 512;   // larger ND blocks are split into a chain
-constexpr int TAPE_CHUNK_WORDS = 256; // 2 KB bulk-copy granularity of the tape ring
-constexpr int TAPE_SLOT_HEADER = 4;   // words of a slot header
-constexpr int TAPE_ROUND_HEADER = 12; // words before the first iteration of a round
-// (both multiples of 4: every iteration starts 32-byte aligned in the ring, so the
-//  128-bit loads of a lane's tile column never straddle the ring's end)
+constexpr int TAPE_REC_HEADER = 16;   // words before the tile values of a record
+inline int tape_record_words(int dh) { return TAPE_REC_HEADER + 8 * dh * dh; }
 
 enum TapeType : int { TAPE_FWD = 0, TAPE_MID = 1, TAPE_BWD = 2 };
 
@@ -59,7 +57,7 @@ struct AgentTape {
   int k = 0, nblocks = 0, nwarps = 0, dh = 0;
   int nslots = 0;
   int nlev[2] = {0, 0};
-  std::vector<std::vector<uint64_t>> warp_tape;  // nwarps tapes, padded to whole chunks
+  std::vector<std::vector<uint64_t>> warp_tape;  // nwarps tapes, whole records
   int64_t stored_values = 0;  // factor values on the tapes, both directions (incl. padding)
   // cost model of the schedule: sum over slots of the busiest warp's
   // iterations / rounds, and the perfectly balanced iteration count

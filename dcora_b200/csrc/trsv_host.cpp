@@ -459,52 +459,59 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
                 sl, (int)sl < Lf - 1 ? "fwd" : (int)sl == Lf - 1 ? "mid" : "bwd", tasks.size(),
                 (long long)total, maxtask, rounds.size(), maxit, maxrounds, (long long)ideal);
     }
-    for (int wi = 0; wi < nwarps; ++wi) {
-      std::vector<uint64_t> &tp = out->warp_tape[wi];
-      tp.push_back(pack2((int)warp_rounds[wi].size(), 0));
-      for (int z = 1; z < TAPE_SLOT_HEADER; ++z) tp.push_back(0);
-      for (int ri : warp_rounds[wi]) {
-        const Round &rd = rounds[ri];
-        tp.push_back(pack2(rd.niter, rd.gpt | (rd.type << 8)));
+    const int recw = tape_record_words(dh);
+    auto emit_round = [&](std::vector<uint64_t> &tp, const Round *rd, bool last) {
+      // rd == nullptr: a zero record (a warp without work in this slot still meets the barrier)
+      const int niter = rd ? rd->niter : 1, gpt = rd ? rd->gpt : 1, type = rd ? rd->type : TAPE_FWD;
+      for (int it = 0; it < niter; ++it) {
+        const size_t w0 = tp.size();
+        tp.resize(w0 + recw, 0);
+        uint64_t *rec = &tp[w0];
+        int c[8];
+        const double *vp[8];
         for (int g = 0; g < 8; ++g) {
-          const int ti = g / rd.gpt;
-          if (ti < (int)rd.tasks.size()) {
-            const Task &tk = tasks[rd.tasks[ti]];
-            tp.push_back(pack2(R0 + tk.r0, tk.nrows));
-          } else {
-            tp.push_back(pack2(-1, 0));
+          const int ti = g / gpt, gg = g % gpt;
+          c[g] = R0;  // padding: any valid row, zero tile
+          vp[g] = nullptr;
+          if (rd && ti < (int)rd->tasks.size()) {
+            const Task &tk = tasks[rd->tasks[ti]];
+            const int q = it * gpt + gg;
+            if (q < tk.ntiles()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
           }
         }
-        for (int z = 9; z < TAPE_ROUND_HEADER; ++z) tp.push_back(0);
-        for (int it = 0; it < rd.niter; ++it) {
-          int c[8];
-          const double *vp[8];
+        for (int g = 0; g < 8; g += 2) rec[g / 2] = pack2(c[g], c[g + 1]);
+        if (it == 0) {
+          rec[4] = pack2(niter, gpt | (type << 8) | ((last ? 1 : 0) << 16));
           for (int g = 0; g < 8; ++g) {
-            const int ti = g / rd.gpt, gg = g % rd.gpt;
-            c[g] = R0;  // padding: any valid row, zero tile
-            vp[g] = nullptr;
-            if (ti < (int)rd.tasks.size()) {
-              const Task &tk = tasks[rd.tasks[ti]];
-              const int q = it * rd.gpt + gg;
-              if (q < tk.ntiles()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
+            const int ti = g / gpt;
+            if (rd && ti < (int)rd->tasks.size()) {
+              const Task &tk = tasks[rd->tasks[ti]];
+              rec[5 + g] = pack2(R0 + tk.r0, tk.nrows);
+            } else {
+              rec[5 + g] = pack2(-1, 0);
             }
           }
-          for (int g = 0; g < 8; g += 2) tp.push_back(pack2(c[g], c[g + 1]));
-          // lane (group g, column bb) owns DH consecutive words: its column of the
-          // tile, rows 0..DH-1 (for DH = 4: two 128-bit shared loads per iteration)
-          for (int g = 0; g < 8; ++g)
-            for (int bb = 0; bb < dh; ++bb)
-              for (int a = 0; a < dh; ++a)
-                tp.push_back(dbits(vp[g] ? vp[g][a * dh + bb] : 0.0));
-          out->stored_values += 8 * bs;
         }
+        // lane (group g, column bb) owns DH consecutive words: its column of the
+        // tile, rows 0..DH-1 (for DH = 4: two 128-bit shared loads per iteration)
+        uint64_t *v = rec + TAPE_REC_HEADER;
+        for (int g = 0; g < 8; ++g)
+          for (int bb = 0; bb < dh; ++bb)
+            for (int a = 0; a < dh; ++a)
+              *v++ = dbits(vp[g] ? vp[g][a * dh + bb] : 0.0);
+        if (rd) out->stored_values += 8 * bs;
       }
+    };
+    for (int wi = 0; wi < nwarps; ++wi) {
+      std::vector<uint64_t> &tp = out->warp_tape[wi];
+      const std::vector<int> &wr = warp_rounds[wi];
+      if (wr.empty()) emit_round(tp, nullptr, true);
+      for (size_t q = 0; q < wr.size(); ++q) emit_round(tp, &rounds[wr[q]], q + 1 == wr.size());
     }
     // warps of a larger launch cluster than this agent's own (batches mix
     // agent sizes; the work split of an agent depends on the agent alone, so
     // its result does not depend on what it is batched with): barriers only
-    for (int wi = nwarps; wi < nwarps_total; ++wi)
-      for (int z = 0; z < TAPE_SLOT_HEADER; ++z) out->warp_tape[wi].push_back(0);
+    for (int wi = nwarps; wi < nwarps_total; ++wi) emit_round(out->warp_tape[wi], nullptr, true);
   }
   if (stats)
     fprintf(stderr, "[tape] k %d blocks %d levels %d/%d slots %d: busiest-warp iterations %lld "
@@ -512,8 +519,6 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
             k, nb, Lf, Lb, out->nslots, (long long)out->crit_iters, (long long)out->ideal_iters,
             (long long)out->crit_rounds, (long long)out->stored_values,
             2 * (long long)F.Lx.size());
-  for (std::vector<uint64_t> &tp : out->warp_tape)
-    while (tp.size() % TAPE_CHUNK_WORDS) tp.push_back(0);
   return DCORA_OK;
 }
 
@@ -521,33 +526,35 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
 // device; inside a slot no task reads what another one writes).
 void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offset,
                            const double *b, double *x, double *T, double *X) {
-  const int dh = S.dh, bs = dh * dh, nw = S.nwarps, R0 = row_offset;
+  const int dh = S.dh, nw = S.nwarps, R0 = row_offset;
   for (int f = 0; f < S.k; ++f) T[R0 + f] = b[F.perm[f]];
+  const int recw = tape_record_words(dh);
   std::vector<size_t> pos(nw, 0);
   for (int sl = 0; sl < S.nslots; ++sl) {
     for (int wi = 0; wi < nw; ++wi) {
       const std::vector<uint64_t> &tp = S.warp_tape[wi];
       size_t &p = pos[wi];
-      const int nrounds = lo32(tp[p]);
-      p += TAPE_SLOT_HEADER;
-      for (int rd = 0; rd < nrounds; ++rd) {
-        const int niter = lo32(tp[p]);
-        const int gpt = hi32(tp[p]) & 0xff, type = hi32(tp[p]) >> 8;
+      for (bool last = false; !last;) {
+        const uint64_t *h = &tp[p];
+        const int niter = lo32(h[4]), cw = hi32(h[4]);
+        const int gpt = cw & 0xff, type = (cw >> 8) & 0xff;
+        last = ((cw >> 16) & 1) != 0;
         int r0[8], nrows[8];
-        for (int g = 0; g < 8; ++g) { r0[g] = lo32(tp[p + 1 + g]); nrows[g] = hi32(tp[p + 1 + g]); }
-        p += TAPE_ROUND_HEADER;
+        for (int g = 0; g < 8; ++g) { r0[g] = lo32(h[5 + g]); nrows[g] = hi32(h[5 + g]); }
         const double *src = type == TAPE_BWD ? X : T;
         double *dst = type == TAPE_FWD ? T : X;
         const bool accumulate = type != TAPE_MID;
         std::vector<double> acc(8 * 4, 0.0);
         for (int it = 0; it < niter; ++it) {
+          const uint64_t *rec = &tp[p];
           int c[8];
-          for (int g = 0; g < 8; g += 2) { c[g] = lo32(tp[p]); c[g + 1] = hi32(tp[p]); ++p; }
+          for (int g = 0; g < 8; g += 2) { c[g] = lo32(rec[g / 2]); c[g + 1] = hi32(rec[g / 2]); }
+          const uint64_t *v = rec + TAPE_REC_HEADER;
           for (int g = 0; g < 8; ++g)
             for (int a = 0; a < dh; ++a)
               for (int bb = 0; bb < dh; ++bb)
-                acc[g * 4 + a] += bitsd(tp[p + (size_t)(g * dh + bb) * dh + a]) * src[c[g] + bb];
-          p += 8 * bs;
+                acc[g * 4 + a] += bitsd(v[(size_t)(g * dh + bb) * dh + a]) * src[c[g] + bb];
+          p += recw;
         }
         for (int g = 0; g < 8; g += gpt) {
           if (r0[g] < 0) continue;
