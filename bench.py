@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-agents", type=int, default=2)
+    ap.add_argument("--cpu-sample-agents", type=int, default=32)
     ap.add_argument("--kernel-iters", type=int, default=20)
     ap.add_argument("--ttc-grid", type=int, default=12,
                     help="side of the single-agent grid of the time-to-certified leg (0: skip)")
@@ -68,11 +68,11 @@ def peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def k1_traffic(args, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one full-batch K1 launch on the default
-    workload, from the committed ncu --set full capture (profiles/k1_traffic.json); null for
-    any other workload / GPU count (no capture)."""
-    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+def kernel_traffic(name, args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one whole-batch launch of a kernel on
+    the default workload, from the committed ncu --set full capture
+    (profiles/<name>_traffic.json); null for any other workload / GPU count (no capture)."""
+    path = os.path.join(ROOT, "profiles", name + "_traffic.json")
     if world != 1 or (args.grid, args.agents, args.rank, args.range_fraction) != (100, 256, 5, 0.1):
         return None
     try:
@@ -151,6 +151,23 @@ def initial_X(args, meas, idx, gp):
     return synthetic.lifted_initial_guess(meas, idx, gp, args.grid, args.rank)
 
 
+def workload_config(args, meas, gp, ncolors):
+    """The `config` object: identical in both arms (same workload, same algorithm)."""
+    return {
+        "workload": f"synthetic {args.grid}^3-pose 3D grid, {int(args.range_fraction * 100)}% range edges, "
+                    f"{args.agents} agents, r={args.rank} (BASELINE.json configs[4])",
+        "poses": int(meas.n), "pose_edges": int(len(meas.pp_i)),
+        "range_edges": int(len(meas.rg_i)), "agents": args.agents, "r": args.rank,
+        "K": int(gp.K), "nnz_Q": int(gp.Q().nnz), "colours": int(ncolors),
+        "step": "one RBCD iteration: every agent once (colour by colour of the robot graph: "
+                "exchange public states, rebuild G, one QuadraticOptimizer::optimize) + the "
+                "global cost / gradient norm (examples/MultiRobotExample.cpp:223-307)",
+        "ropt": "default ROptParameters (3 RTR x 50 tCG, tol 1e-2), TimeBound disabled",
+        "init": "spanning-tree composition of measurements, lifted with [I;0]",
+        "l2": "operands (Q 0.76 GB, factor 5.9 GB, X) exceed the 126 MB L2; no flush needed",
+    }
+
+
 # --------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -189,88 +206,86 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg (value)
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(vs):
+        t = torch.tensor([float(v) for v in vs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    # ---- warm-up, then the iterate both timed legs start from (kept in pinned host memory)
     hist = []
     for _ in range(args.warmup):
         S.iterate()
         hist.append(S.monitor())
+    p = S.plan
+    hstart = torch.empty((p.K, args.rank), dtype=torch.float64).pin_memory()
+    hwork = torch.empty((p.K, args.rank), dtype=torch.float64).pin_memory()
+    hstart_np, hwork_np = hstart.numpy().T, hwork.numpy().T     # (r, K) column-major views
+    S.store_host_X(hstart_np)
+
+    # ---- device-resident leg (value)
     ext = torch.cuda.ExternalStream(S.P.stream(), device=torch.device("cuda", local_rank))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    l0 = S.P.launch_count()
-    u0 = S.agent_updates
+    l0, u0, i0, o0 = S.P.launch_count(), S.agent_updates, S.inner_iterations, S.outer_iterations
     e0.record(ext)
     tw0 = time.perf_counter()
+    vhist = []
     for _ in range(args.steps):
         S.iterate()
-        hist.append(S.monitor())
+        vhist.append(S.monitor())
     e1.record(ext)
     barrier()
     wall_ms = (time.perf_counter() - tw0) * 1e3
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    launches = S.P.launch_count() - l0
-    updates = S.agent_updates - u0
-    t = torch.tensor([max(dev_ms, wall_ms), float(launches), float(updates)],
-                     dtype=torch.float64, device="cuda")
-    if world > 1:
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        total_ms, launches, updates = float(tm[0]), int(ts[1]), int(ts[2])
-    else:
-        total_ms = float(t[0])
+    total_ms = allmax(max(dev_ms, wall_ms))
+    launches, updates, inner, outer = allsum([S.P.launch_count() - l0, S.agent_updates - u0,
+                                              S.inner_iterations - i0, S.outer_iterations - o0])
     ms_per_step = total_ms / args.steps
     value = 1e3 / ms_per_step
+    hist += vhist
     log(f"value leg: {ms_per_step:.1f} ms/step  cost {hist[0][0]:.6e} -> {hist[-1][0]:.6e}  "
-        f"gradnorm {hist[0][1]:.3e} -> {hist[-1][1]:.3e}")
+        f"gradnorm {hist[0][1]:.3e} -> {hist[-1][1]:.3e}  tCG iterations/step {inner / args.steps:.0f}")
 
-    # ---- end-to-end leg: host buffers in, host buffers out, every step
+    # ---- end-to-end leg: the same steps from the same iterate, but the iterate lives in
+    #      (pinned) host memory between steps: uploaded through the C-ABI at the start of
+    #      every step, read back with the step's cost / gradient norm at its end
     e2e = None
     if not args.no_e2e:
-        p = S.plan
-        # two pinned host buffers: the iterate goes host -> device at the start of every step
-        # and device -> host at its end; the buffers swap roles between steps (the host
-        # side of a caller keeps the result where the library wrote it)
-        hbuf = [torch.from_numpy(np.ascontiguousarray(S.get_X().T)).pin_memory(), None]
-        hbuf[1] = torch.empty_like(hbuf[0]).pin_memory()
-        res_h = torch.zeros(2, dtype=torch.float64).pin_memory()
-        xdev = torch.empty_like(S.X)
-        xh = hbuf[0]
+        hwork.copy_(hstart)
+        res_h = np.zeros(2)
+        ehist = []
 
         def e2e_step():
-            xdev.copy_(hbuf[0], non_blocking=True)      # H2D of this step's input
-            S.set_device_X(xdev)
-            torch.cuda.current_stream().synchronize()
+            S.load_host_X(hwork_np)                     # H2D of this step's input
             S.iterate()
-            f, g = S.monitor()
-            hbuf[1].copy_(S.X, non_blocking=True)       # D2H of this step's result
-            res_h[0], res_h[1] = f, g
-            torch.cuda.current_stream().synchronize()
-            hbuf[0], hbuf[1] = hbuf[1], hbuf[0]
-        for _ in range(min(1, args.warmup)):
-            e2e_step()
+            res_h[:] = S.monitor()
+            S.store_host_X(hwork_np)                    # D2H of this step's result
+            ehist.append(tuple(res_h))
         barrier()
         tw0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         barrier()
-        ms = (time.perf_counter() - tw0) * 1e3
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt[0]) / args.steps
-        nbytes = xh.numel() * 8
+        e2e_ms = allmax((time.perf_counter() - tw0) * 1e3) / args.steps
+        nbytes = hwork.numel() * 8
+        same = all(abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) for a, b in zip(ehist, vhist))
         e2e = {"value": 1e3 / e2e_ms, "unit": "RBCD iterations/s",
                "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes + 16),
-               "ms_per_step": e2e_ms}
-        log(f"e2e leg: {e2e_ms:.1f} ms/step")
+               "ms_per_step": e2e_ms, "same_iterates_as_value_leg": bool(same)}
+        log(f"e2e leg: {e2e_ms:.1f} ms/step (same trajectory as the value leg: {same})")
 
     # ---- roofline of the hot-path kernels (rank 0's local batch, device-resident,
-    #      operands > L2: Q + X are far larger than 126 MB at the default size)
+    #      operands > L2: Q, the factor tapes and X are far larger than 126 MB at the default size)
     peak, peak_src = peaks()
     kern = {}
     for kind in ("spmm", "precond", "project", "retract", "dot", "axpby", "rhess"):
@@ -280,11 +295,12 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args, gp, S, X0, log)
+        Xs = np.empty((args.rank, gp.K), order="F") if world == 1 else None
+        if world == 1:
+            Xs[:] = hstart_np
+        cpu = cpu_baseline(args, gp, Xs if Xs is not None else X0, log)
 
-    # ---- time-to-certified-solution (BASELINE.json metric, second half): single-agent
-    #      Riemannian staircase + certificate on a small range-aided grid, everything counted
-    #      (assembly, Cholesky + tape build + upload, solve, certification)
+    # ---- time-to-certified-solution (BASELINE.json metric, second half)
     ttc = None
     if rank == 0 and args.ttc_grid > 0:
         try:
@@ -292,13 +308,14 @@ def run_ours(args):
             import ttc as ttc_mod
             ttc = ttc_mod.run(args.ttc_grid, args.rank, args.range_fraction, args.seed)
             ttc.pop("levels", None)
-            log(f"time-to-certified ({ttc['poses']} poses): {ttc['seconds']:.2f} s "
-                f"(setup {ttc['factor_upload_s']:.2f} s, solve+certify {ttc['solve_certify_s']:.2f} s), "
+            log(f"time-to-certified ({ttc['poses']} poses): {ttc['seconds']:.2f} s, "
                 f"certified={ttc['certified']} rank={ttc['rank']}")
         except Exception as e:  # pragma: no cover
             ttc = {"error": repr(e)}
 
     if rank == 0:
+        cfg = workload_config(args, meas, gp, S.plan.num_colors)
+        dom = "precond"
         out = {
             "metric": "RBCD iterations/s",
             "value": value,
@@ -311,30 +328,28 @@ def run_ours(args):
             "dtype": "f64",
             "data": "synthetic",
             "impl": "ours",
-            "config": {
-                "workload": f"synthetic {args.grid}^3-pose 3D grid, {int(args.range_fraction * 100)}% range edges, "
-                            f"{args.agents} agents, r={args.rank} (BASELINE.json configs[4])",
-                "poses": int(meas.n), "pose_edges": int(len(meas.pp_i)),
-                "range_edges": int(len(meas.rg_i)), "agents": args.agents, "r": args.rank,
-                "K": int(gp.K), "nnz_Q": int(gp.Q().nnz), "colours": int(S.plan.num_colors),
-                "parallelism": f"agents partitioned over {world} GPU(s), all-gather of public states per colour step",
-                "l2": "operands (Q 0.76 GB + X) exceed the 126 MB L2; no flush needed",
-                "ropt": "default ROptParameters (3 RTR x 50 tCG, tol 1e-2), TimeBound disabled",
-                "init": "spanning-tree composition of measurements, lifted with [I;0]",
-            },
+            "config": cfg,
+            "parallelism": f"agents partitioned over {world} GPU(s), all-gather of public states per colour step",
             "agent_updates_per_s": updates / (total_ms / 1e3),
+            "inner_iterations_per_step": inner / args.steps,
+            "outer_iterations_per_step": outer / args.steps,
+            "k5_solves_per_step": inner / args.steps,
+            "k5_solves_note": "agent-level preconditioner applications: one per tCG iteration "
+                              "(the initial z = P^-1 r of a tCG run + one per continued iteration)",
             "cost": {"first": 2 * hist[0][0], "last": 2 * hist[-1][0]},
             "gradnorm": {"first": hist[0][1], "last": hist[-1][1]},
             "setup_s": setup_s,
             "timing": {"device_ms": dev_ms, "wall_ms": wall_ms},
             "clocks": clocks,
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "bsr_spmm_kernel (Q-SpMM, K1)", "bound": "hbm",
-                         "achieved": kern["spmm"]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kern["spmm"]["frac"], "traffic": k1_traffic(args, world),
+            "roofline": {"kernel": "trsv_tape_kernel (K5, preconditioner solve: the dominant kernel "
+                                   "of an RBCD iteration), whole batch in one launch",
+                         "bound": "hbm",
+                         "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kern[dom]["frac"], "traffic": kernel_traffic("k5", args, world),
                          "peak_source": peak_src,
-                         "algorithmic_bytes": kern["spmm"]["bytes"],
-                         "launch_ms": kern["spmm"]["ms"]},
+                         "algorithmic_bytes": kern[dom]["bytes"],
+                         "launch_ms": kern[dom]["ms"]},
             "kernels": kern,
         }
         if ttc is not None:
@@ -349,95 +364,37 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------
-def _oracle_blocks(gp, agents, r):
-    """Oracle agent problems for a sample of agents (same Q blocks)."""
-    import scipy.sparse as sp
-    from oracle import manifold as mf, rbcd as orbcd
-    diag, cross = gp.split(agents=agents)
-    blocks = {}
-    for a in agents:
-        L = mf.Layout(r, gp.d, int(gp.n_a[a]), int(gp.l_a[a]), int(gp.b_a[a]), ra=gp.ra)
-        rowptr, col, val = diag[a]
-        Q = sp.csr_matrix((val, col, rowptr), shape=(L.k, L.k))
-        blocks[a] = orbcd.AgentBlock(L, Q, int(gp.coff[a]), reg=0.1)
-    return blocks, cross
-
-
-def _cpu_agent_update(args_tuple):
-    """One Agent::updateX on the CPU oracle (worker for the reference arm)."""
-    (rowptr, col, val, Ga, Xa, r, d, n, l, b, ra, reg) = args_tuple
-    import scipy.sparse as sp
-    from oracle import manifold as mf, solver
-    try:
-        # one BLAS thread per worker: the pool already uses every core (a forked worker
-        # inherits the parent's multi-threaded BLAS pool and would oversubscribe 8x)
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=1)
-    except Exception:
-        pass
-    L = mf.Layout(r, d, n, l, b, ra=ra)
-    Q = sp.csr_matrix((val, col, rowptr), shape=(L.k, L.k))
-    P = solver.QuadraticProblem(L, Q, G=Ga, precond_reg=reg)
-    P._factor()                       # set-up (excluded from the timed update)
+def cpu_baseline(args, gp, X, log):
+    """The CPU path (oracle/native: C++ -O3 port of Agent::updateX, `kind: port`), ONE
+    thread, on a bounded sample of the same workload: `cpu_sample_agents` agent updates from
+    the iterate the timed GPU legs start from; one RBCD iteration = `agents` updates."""
+    from oracle.cpu_rbcd import CpuRBCD
+    sample = sorted(set(int(a) for a in np.linspace(0, args.agents - 1, args.cpu_sample_agents)))
+    C = CpuRBCD(gp, args.rank, threads=1, agents=sample, log=log)
+    C.set_X(X)
     t0 = time.perf_counter()
-    opt = solver.QuadraticOptimizer(P, solver.ROptParameters())
-    Xn = opt.optimize(Xa)
-    return time.perf_counter() - t0, opt.result.inner_iters
-
-
-def _reg_for(gp, S, a):
-    if S is not None and S.plan.a0 <= a < S.plan.a1:
-        return S.P.precond_reg(a - S.plan.a0)
-    return 0.1
-
-
-def cpu_sample(args, gp, X, agents, S=None, procs=1):
-    """Time Agent::updateX of the oracle for a sample of agents.  Returns the
-    per-update seconds list."""
-    diag, cross = gp.split(agents=agents)
-    Ct = cross.T.tocsr()
-    jobs = []
-    for a in agents:
-        c0, c1 = int(gp.coff[a]), int(gp.coff[a + 1])
-        Ga = (Ct[c0:c1] @ X.T).T
-        rowptr, col, val = diag[a]
-        jobs.append((rowptr, col, val, Ga, np.ascontiguousarray(X[:, c0:c1]), args.rank, gp.d,
-                     int(gp.n_a[a]), int(gp.l_a[a]), int(gp.b_a[a]), gp.ra, _reg_for(gp, S, a)))
-    if procs <= 1:
-        return [_cpu_agent_update(j) for j in jobs]
-    import multiprocessing as mp
-    with mp.get_context("fork").Pool(procs) as pool:
-        return pool.map(_cpu_agent_update, jobs)
-
-
-def cpu_baseline(args, gp, S, X0, log):
-    """Oracle port, ONE thread, bounded sample: `cpu_sample_agents` agent
-    updates of the same workload; extrapolated to a full iteration
-    (= `agents` updates)."""
-    try:
-        from threadpoolctl import threadpool_limits
-        ctx = threadpool_limits(limits=1)
-    except Exception:
-        import contextlib
-        ctx = contextlib.nullcontext()
-    sample = list(np.linspace(0, args.agents - 1, args.cpu_sample_agents).astype(int))
-    sample = sorted(set(int(a) for a in sample))
-    with ctx:
-        res = cpu_sample(args, gp, X0, sample, S=S, procs=1)
-    per = float(np.mean([t for t, _ in res]))
+    for a in sample:                 # one at a time: each sees the others' previous state
+        C.update_agents([a])
+    dt = time.perf_counter() - t0
+    per = dt / len(sample)
     it_s = 1.0 / (per * args.agents)
-    log(f"cpu baseline: {per:.2f} s per agent update (1 thread) -> {it_s:.5f} iterations/s")
+    log(f"cpu baseline: {per * 1e3:.0f} ms per agent update (1 thread, native oracle) -> "
+        f"{it_s:.5f} iterations/s")
     return {"value": it_s, "unit": "RBCD iterations/s", "cores": 1, "kind": "port",
-            "sample": f"{len(sample)} of {args.agents} agent updates (agents {sample}) of the same "
-                      f"workload from the same initial iterate, numpy/scipy oracle, 1 thread; "
-                      f"one iteration = {args.agents} updates; factorisation excluded",
-            "seconds_per_agent_update": per}
+            "sample": f"{len(sample)} of {args.agents} agent updates (agents {sample[0]}..{sample[-1]}, evenly "
+                      f"spaced) from the iterate the timed legs start from; C++ -O3 oracle "
+                      f"(oracle/native: CSR SpMM, sparse Cholesky solve, RTR/tCG), 1 thread; one "
+                      f"iteration = {args.agents} updates; factorisation and the per-iteration "
+                      f"global cost evaluation excluded",
+            "seconds_per_agent_update": per,
+            "inner_iterations_per_update": C.stats["inner"] / max(1, C.stats["updates"])}
 
 
 def run_reference(args):
-    """The reference's CPU path (oracle port: the reference itself cannot be
-    built here or on the GPU box -- Eigen/SuiteSparse/ROPTLIB/Spectra absent),
-    all host cores, bounded sample per step."""
+    """The reference's CPU path -- the C++ -O3 oracle port of Agent::updateX driven by the
+    reference's loop (the reference itself cannot be built here or on the GPU box:
+    Eigen/SuiteSparse/ROPTLIB/Spectra absent) -- on all host cores, FULL steps of the same
+    workload, same colouring / parameters / start as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -445,40 +402,42 @@ def run_reference(args):
     def log(msg):
         print("[bench-ref] " + msg, file=sys.stderr, flush=True)
 
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle.cpu_rbcd import CpuRBCD
     meas, gt, idx, gp = build_problem(args, log)
     X0 = initial_X(args, meas, idx, gp)
-    cores = os.cpu_count() or 1
-    per_step = max(cores, 2)
-    times = []
-    total = args.warmup + args.steps
-    stride = max(1, args.agents // (per_step * total))
-    for s in range(total):
-        agents = [(s * per_step + j) * stride % args.agents for j in range(per_step)]
-        agents = sorted(set(agents))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    C = CpuRBCD(gp, args.rank, threads=cores, log=log)
+    C.set_X(X0)
+    hist, times = [], []
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            base = dict(C.stats)
         t0 = time.perf_counter()
-        res = cpu_sample(args, gp, X0, agents, procs=cores)
-        wall = time.perf_counter() - t0
-        busy = float(np.sum([t for t, _ in res]))
-        # throughput of the pool while it was solving: updates / (sum of solve time / cores)
-        times.append(busy / cores / len(agents))
-        log(f"step {s}: {len(agents)} updates, {busy / len(agents):.2f} s each, wall {wall:.1f}s")
+        C.iterate()
+        hist.append(C.monitor())
+        times.append(time.perf_counter() - t0)
+        log(f"step {s}: {times[-1]:.2f} s  cost {2 * hist[-1][0]:.6e}  gradnorm {hist[-1][1]:.3e}")
     per = float(np.mean(times[args.warmup:]))
-    ms_per_step = per * args.agents * 1e3
-    value = 1e3 / ms_per_step
+    ms_per_step = per * 1e3
+    value = 1.0 / per
+    st = {k: C.stats[k] - base[k] for k in base}
     out = {
         "metric": "RBCD iterations/s", "value": value, "unit": "RBCD iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {
-            "workload": f"synthetic {args.grid}^3-pose 3D grid, {int(args.range_fraction * 100)}% range edges, "
-                        f"{args.agents} agents, r={args.rank} (BASELINE.json configs[4])",
-            "poses": int(meas.n), "agents": args.agents, "r": args.rank},
+        "config": workload_config(args, meas, gp, int(C.colors.max()) + 1),
+        "inner_iterations_per_step": st["inner"] / args.steps,
+        "outer_iterations_per_step": st["outer"] / args.steps,
+        "k5_solves_per_step": st["precond"] / args.steps,
+        "cost": {"first": 2 * hist[0][0], "last": 2 * hist[-1][0]},
+        "gradnorm": {"first": hist[0][1], "last": hist[-1][1]},
+        "setup_s": C.setup_s,
+        "step_seconds": times,
         "cpu_baseline": {"value": value, "unit": "RBCD iterations/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} agent updates per step spread over {cores} processes "
-                                   f"(one agent per core), extrapolated to {args.agents} updates per "
-                                   f"iteration; numpy/scipy oracle; factorisation excluded"},
+                         "sample": f"full RBCD iterations ({args.agents} agent updates + global cost / "
+                                   f"gradient norm each): C++ -O3 oracle (oracle/native) per agent "
+                                   f"update, the agents of a colour dealt to {cores} threads"},
         "e2e": {"value": value, "unit": "RBCD iterations/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

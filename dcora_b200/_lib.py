@@ -36,6 +36,16 @@ class ROptResult(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+# numpy view of an array of ROptResult
+import numpy as _np
+ROPT_RESULT_DTYPE = _np.dtype([("success", "<i4"), ("tCGStatus", "<i4"), ("fInit", "<f8"),
+                               ("gradNormInit", "<f8"), ("fOpt", "<f8"), ("gradNormOpt", "<f8"),
+                               ("elapsedMs", "<f8"), ("outer_iterations", "<i4"),
+                               ("inner_iterations", "<i4"), ("accepted", "<i4"),
+                               ("reserved", "<i4")])
+assert ROPT_RESULT_DTYPE.itemsize == C.sizeof(ROptResult)
+
+
 class HaloSegment(C.Structure):
     _fields_ = [("n", C.c_int32), ("l", C.c_int32), ("b", C.c_int32)]
 
@@ -88,6 +98,8 @@ SYMBOLS = {
     "dcora_problem_update_G": (C.c_int, [VP, VP, VP, c_uint8_p]),
     "dcora_problem_pack_columns": (C.c_int, [VP, VP, c_int32_p, C.c_int64, VP]),
     "dcora_problem_set_iterate_tracking": (C.c_int, [VP, C.c_int32]),
+    "dcora_problem_load_iterate": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_store_iterate": (C.c_int, [VP, VP, VP]),
     "dcora_problem_cost_terms": (C.c_int, [VP, VP, c_double_p, c_double_p]),
     "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
                                                 c_uint8_p, VP]),

@@ -357,6 +357,19 @@ class QuadraticProblem:
         device buffer yourself."""
         check(self.lib.dcora_problem_set_iterate_tracking(self.h, int(bool(on))))
 
+    def load_iterate(self, X_host, X_device):
+        """numpy (r, K) column-major (pinned or pageable) -> CUDA tensor (K, r)."""
+        a = np.asarray(X_host)
+        assert a.dtype == np.float64 and a.shape == (self.r, self.K) and a.flags.f_contiguous
+        d = _Arg(X_device, self.r, self.K, out=True)
+        check(self.lib.dcora_problem_load_iterate(self.h, a.ctypes.data_as(C.c_void_p), d.ptr))
+
+    def store_iterate(self, X_device, X_host):
+        a = X_host
+        assert a.dtype == np.float64 and a.shape == (self.r, self.K) and a.flags.f_contiguous
+        d = _Arg(X_device, self.r, self.K)
+        check(self.lib.dcora_problem_store_iterate(self.h, d.ptr, a.ctypes.data_as(C.c_void_p)))
+
     def cost_terms(self, X):
         a = _Arg(X, self.r, self.K)
         q = (C.c_double * self.A)()

@@ -9,6 +9,7 @@
 // (QuadraticProblem.cpp:138-234).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "solver.cuh"
@@ -499,13 +500,54 @@ extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
   res->matvecs = matvecs;
   res->restarts = restarts;
   // Verdict.  `lam` is a Rayleigh quotient, i.e. an UPPER bound of lambda_min(S): a value
-  // below -eta proves "not PSD" whether or not the iteration converged, but "PSD" may only
-  // be claimed from a converged extreme Ritz pair whose residual leaves a margin (the
-  // reference decides with an exact Cholesky of S + eta I, DCORA_utils.cpp:1713-1747).
-  // Anything else is reported as not certified with converged = 0.
-  const bool proven_psd = converged && (lam - resid + eta > 0.0);
-  if (!proven_psd && lam + eta > 0.0) res->converged = 0;
-  res->is_psd = proven_psd ? 1 : 0;
+  // below -eta proves "not PSD" whether or not the iteration converged.  "PSD" is decided
+  // like the reference does (fastVerification -> isSparseSymmetricMatrixPSD,
+  // DCORA_utils.cpp:1713-1747): by an exact sparse Cholesky of S + eta I on the host, unless
+  // the extreme Ritz pair has converged with a margin that makes the test redundant.
+  int proven_psd = 0;
+  if (lam + eta > 0.0) {
+    if (converged && lam - resid + eta > 0.0 && !getenv("DCORA_CERTIFY_ALWAYS_CHOLESKY")) {
+      proven_psd = 1;
+    } else if (!M.hostQ_ptr.empty()) {
+      // S + eta I = Q - Lambda + eta I in the internal ordering (duplicate entries add up)
+      std::vector<double> hl((size_t)p->r * K);
+      CERT_CUDA(cudaMemcpyAsync(hl.data(), Lam, sizeof(double) * hl.size(), cudaMemcpyDeviceToHost,
+                                p->stream));
+      CERT_CUDA(cudaStreamSynchronize(p->stream));
+      const int k = (int)K, dd = M.d, dhh = M.d + 1, np = M.n[0], nl = M.l[0];
+      std::vector<int> Ap(k + 1, 0);
+      for (int i = 0; i < k; ++i) {
+        int extra = 1;                                   // eta on the diagonal
+        if (i < dhh * np) { if (i % dhh < dd) extra += dd; }
+        else if (i < dhh * np + nl) extra += 1;
+        Ap[i + 1] = Ap[i] + (M.hostQ_ptr[i + 1] - M.hostQ_ptr[i]) + extra;
+      }
+      std::vector<int> Ai(Ap[k]);
+      std::vector<double> Ax(Ap[k]);
+      for (int i = 0; i < k; ++i) {
+        int w = Ap[i];
+        for (int q = M.hostQ_ptr[i]; q < M.hostQ_ptr[i + 1]; ++q) {
+          Ai[w] = M.hostQ_col[q]; Ax[w] = M.hostQ_val[q]; ++w;
+        }
+        Ai[w] = i; Ax[w] = eta; ++w;
+        if (i < dhh * np) {
+          const int pi = i / dhh, a = i % dhh;
+          if (a < dd) {
+            // Lambda block of pose pi lives at pb = (pi * dh) * r: entry [a * d + b] = S[b][a]
+            const size_t pb = (size_t)(pi * dhh) * p->r;
+            for (int b = 0; b < dd; ++b) { Ai[w] = pi * dhh + b; Ax[w] = -hl[pb + a * dd + b]; ++w; }
+          }
+        } else if (i < dhh * np + nl) {
+          Ai[w] = i; Ax[w] = -hl[(size_t)i * p->r]; ++w;
+        }
+      }
+      HostFactor Fs;
+      const int frc = sparse_cholesky(k, Ap, Ai, Ax, dhh, np, &Fs);
+      proven_psd = frc == DCORA_OK ? 1 : 0;
+    }
+  }
+  if (!proven_psd && lam + eta > 0.0 && M.hostQ_ptr.empty()) res->converged = 0;
+  res->is_psd = proven_psd;
   cleanup();
 #undef CERT_CUDA
   return DCORA_OK;

@@ -16,6 +16,7 @@ constexpr int MAX_RANK = 16;      // templated ranks 1..MAX_RANK
 constexpr int POSE_CHUNK = 64;    // poses per chunk (pose region)
 constexpr int EXTRA_CHUNK = 512;  // columns per chunk (sphere / landmark region)
 constexpr int NUM_SMS = 148;      // B200
+constexpr int DCORA_COUNT_RING = 8;  // slots of the solver's lagged "agents still iterating" counts
 
 void set_error(const std::string &msg);
 
@@ -175,6 +176,9 @@ struct DeviceMatrices {
   std::vector<int64_t> coff;
   std::vector<int> n, l, b, poff, agent_chunk0_h, rem_agent_h;
   std::vector<double> reg;  // per agent: regularisation of the factor (<0: none)
+  // single-agent handles: Q as full symmetric CSR in the internal ordering (exact PSD test)
+  std::vector<int> hostQ_ptr, hostQ_col;
+  std::vector<double> hostQ_val;
   bool identity_perm = true;
   int *perm = nullptr;
   int *browptr = nullptr, *bcol = nullptr, *prowcol = nullptr;
@@ -224,6 +228,7 @@ struct dcora_problem {
   double *h_scal = nullptr;        // pinned mirror
   int *flags = nullptr;            // per-agent int flags (device)
   int *h_flags = nullptr;          // pinned mirror
+  cudaEvent_t count_ev[dcora::DCORA_COUNT_RING] = {};  // read-back events of the count ring (solver.cu)
   double *vec(int i);              // lazily allocated workspace vector i
   ~dcora_problem();
 };

@@ -131,11 +131,11 @@ static int alloc_handle_buffers(dcora_problem *p) {
     DCORA_CUDA(cudaMalloc(&p->stage, std::max<size_t>(1, p->vec_len) * sizeof(double)));
   DCORA_CUDA(cudaMalloc(&p->partials, std::max(1, M.nchunks) * NPART * sizeof(double)));
   DCORA_CUDA(cudaMalloc(&p->scal, sizeof(double) * NS * M.A));
-  DCORA_CUDA(cudaMalloc(&p->flags, sizeof(int) * (NF * M.A + 4)));  // + counters
+  DCORA_CUDA(cudaMalloc(&p->flags, sizeof(int) * (NF * M.A + 4 + DCORA_COUNT_RING)));  // + counters
   DCORA_CUDA(cudaMallocHost(&p->h_scal, sizeof(double) * NS * M.A));
-  DCORA_CUDA(cudaMallocHost(&p->h_flags, sizeof(int) * (NF * M.A + 4)));
+  DCORA_CUDA(cudaMallocHost(&p->h_flags, sizeof(int) * (NF * M.A + 4 + DCORA_COUNT_RING)));
   DCORA_CUDA(cudaMemsetAsync(p->scal, 0, sizeof(double) * NS * M.A, p->stream));
-  std::vector<int> fl((size_t)NF * M.A + 4, 0);
+  std::vector<int> fl((size_t)NF * M.A + 4 + DCORA_COUNT_RING, 0);
   for (int a = 0; a < M.A; ++a) { fl[a * NF + F_ALL] = 1; fl[a * NF + F_USER] = 1; }
   DCORA_CUDA(cudaMemcpyAsync(p->flags, fl.data(), fl.size() * sizeof(int),
                              cudaMemcpyHostToDevice, p->stream));
@@ -166,6 +166,7 @@ dcora_problem::~dcora_problem() {
   for (double *w : ws) cudaFree(w);
   cudaFree(G); cudaFree(stage); cudaFree(xe); cudaFree(hstage); cudaFree(pack_idx); cudaFree(partials); cudaFree(scal); cudaFree(flags);
   cudaFreeHost(h_scal); cudaFreeHost(h_flags);
+  for (cudaEvent_t e : count_ev) if (e) cudaEventDestroy(e);
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
 
@@ -262,6 +263,28 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
     }
     DCORA_CUDA(upload(&M->chunk_pose0, pose0));
     DCORA_CUDA(upload(&M->chunk_rem, remr));
+  }
+
+  // ---- centralised problems keep Q on the host (internal ordering): the exact PSD test
+  // of the certificate (dcora_certify) factors S + eta I = Q - Lambda + eta I
+  if (num_agents == 1) {
+    const dcora_agent_desc &g = agents[0];
+    const int k = (d + 1) * g.n + g.l + g.b;
+    std::vector<int> ref2int(k);
+    for (int c = 0; c < k; ++c) ref2int[H.perm[c]] = c;
+    M->hostQ_ptr.assign(k + 1, 0);
+    for (int R = 0; R < k; ++R) M->hostQ_ptr[ref2int[R] + 1] = g.rowptr[R + 1] - g.rowptr[R];
+    for (int i = 0; i < k; ++i) M->hostQ_ptr[i + 1] += M->hostQ_ptr[i];
+    M->hostQ_col.resize(M->hostQ_ptr[k]);
+    M->hostQ_val.resize(M->hostQ_ptr[k]);
+    for (int R = 0; R < k; ++R) {
+      int w = M->hostQ_ptr[ref2int[R]];
+      for (int q = g.rowptr[R]; q < g.rowptr[R + 1]; ++q) {
+        M->hostQ_col[w] = ref2int[g.col[q]];
+        M->hostQ_val[w] = g.val[q];
+        ++w;
+      }
+    }
   }
 
   // ---- preconditioner factors (host) -> device

@@ -212,6 +212,25 @@ int dcora_problem_pack_columns(dcora_problem *p, const double *X, const int32_t 
   return DCORA_OK;
 }
 
+int dcora_problem_load_iterate(dcora_problem *p, const double *X_host, double *X_device) {
+  if (!p || !X_host || !X_device) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  if (X_device == p->tracked) p->tracked = nullptr;
+  DCORA_CUDA(cudaMemcpyAsync(X_device, X_host, sizeof(double) * p->vec_len,
+                             cudaMemcpyHostToDevice, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+int dcora_problem_store_iterate(dcora_problem *p, const double *X_device, double *X_host) {
+  if (!p || !X_host || !X_device) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  DCORA_CUDA(cudaMemcpyAsync(X_host, X_device, sizeof(double) * p->vec_len,
+                             cudaMemcpyDeviceToHost, p->stream));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
 int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,
                              double *lin_out) {
   if (!p || !X) return DCORA_ERR_ARG;

@@ -194,13 +194,9 @@ rtr_cluster_kernel(const ClusterArgs A) {
     if (A.has_factor) {
       rd.start(my_tape, my_nrec);                      // the tape streams from here on
       const long long f0 = A.arow0[agent], f1 = A.arow0[agent + 1];
-      for (long long e = f0 * R + crank * NT + tid; e < f1 * R; e += (long long)CL * NT) {
-        const long long f = e / R;
-        const int q = (int)(e - f * R);
-        A.T[e] = v[(size_t)A.frow_col[f] * R + q];
-      }
+      trsv_permute_rows<R, false>(f0, f1, crank * NT + tid, CL * NT, A.frow_col, v, A.T);
       csync();
-      trsv_run<R, DH, CL>(rd, A.T, A.Xp, no_trace);
+      trsv_run<R, DH, CL>(rd, A.T, A.Xp, (int)f0, no_trace);
       rd.drain();
     }
     for (int k = 0; k < npass; ++k) {

@@ -57,7 +57,7 @@ combine_f_kernel(const int *list, const int *agent_chunk0, const double *partial
 __global__ void __launch_bounds__(128)
 rtr_init_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                 double *scal, double tol, double delta0, double max_delta,
-                int *counters) {
+                int *counter) {
   __shared__ double sm[4];
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   const double gg = agent_sum(agent_chunk0, partials, a, 0, sm);
@@ -77,7 +77,7 @@ rtr_init_kernel(const int *list, const int *agent_chunk0, const double *partials
   f[F_TCG] = 0; f[F_STEP] = 0; f[F_END] = 0;
   f[F_STATUS] = DCORA_TCG_MAXITER;
   f[F_NINNER] = 0; f[F_NOUTER] = 0; f[F_ACCEPT] = 0;
-  if (on) atomicAdd(&counters[0], 1);
+  if (on) atomicAdd(counter, 1);
 }
 
 // start of tCG: partial 0 = <z, r>
@@ -133,7 +133,7 @@ tcg_stepA_kernel(const int *list, const int *agent_chunk0, const double *partial
 // partial 0 = <r, r> after the update
 __global__ void __launch_bounds__(128)
 tcg_stepB_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
-                 double *scal, int j, int min_inner, int max_inner, int *counters) {
+                 double *scal, int j, int min_inner, int max_inner, int *counter) {
   __shared__ double sm[4];
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
@@ -158,7 +158,7 @@ tcg_stepB_kernel(const int *list, const int *agent_chunk0, const double *partial
     }
   }
   f[F_TCG] = on;
-  if (on) atomicAdd(&counters[1], 1);
+  if (on) atomicAdd(counter, 1);
 }
 
 // partial 0 = <z, r> with the new z
@@ -218,7 +218,7 @@ rtr_rho_kernel(const int *list, const int *agent_chunk0, const double *partials,
 // after the gradient at the accepted point: partial 0 = <gf, gf>
 __global__ void __launch_bounds__(128)
 rtr_accept_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
-                  double *scal, int max_iter, int single_mode, int *counters) {
+                  double *scal, int max_iter, int single_mode, int *counter) {
   __shared__ double sm[4];
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
@@ -236,7 +236,7 @@ rtr_accept_kernel(const int *list, const int *agent_chunk0, const double *partia
   }
   if (f[F_NOUTER] >= max_iter) on = 0;
   f[F_OUTER] = on;
-  if (on) atomicAdd(&counters[0], 1);
+  if (on) atomicAdd(counter, 1);
 }
 
 }  // namespace
@@ -259,20 +259,44 @@ int eval_f(dcora_problem *p, const double *X, double *tmp, int slot, int mask_fl
   return launch_combine_f(p, slot, p->has_G ? 1 : 0, mask_flag);
 }
 
-static int read_counters(dcora_problem *p, int *out2) {
-  int *dc = p->flags + (size_t)NF * p->M->A;
-  int *hc = p->h_flags + (size_t)NF * p->M->A;
-  DCORA_CUDA(cudaMemcpyAsync(hc, dc, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-  DCORA_CUDA(cudaStreamSynchronize(p->stream));
-  out2[0] = hc[0]; out2[1] = hc[1];
-  return DCORA_OK;
-}
-
-static int zero_counter(dcora_problem *p, int which) {
-  int *dc = p->flags + (size_t)NF * p->M->A;
-  DCORA_CUDA(cudaMemsetAsync(dc + which, 0, sizeof(int), p->stream));
-  return DCORA_OK;
-}
+// "How many agents go on?" counters.  The host must know them to stop launching, but it
+// must not wait for them: every count lives in its own slot of a small ring, is copied to
+// pinned memory behind the kernel that produces it, and is looked at one loop iteration
+// LATER -- by then the copy has long completed while the GPU is still busy with the work
+// queued in between.  The price is a handful of launches that find every agent switched
+// off when a loop ends (they exit at once).
+struct CountRing {
+  dcora_problem *p;
+  int *dev, *host;
+  int next = 0;
+  explicit CountRing(dcora_problem *p_)
+      : p(p_), dev(p_->flags + (size_t)NF * p_->M->A + 4),
+        host(p_->h_flags + (size_t)NF * p_->M->A + 4) {}
+  // a zeroed slot for the next counting kernel
+  int open(int **dptr) {
+    const int s = next;
+    next = (next + 1) % DCORA_COUNT_RING;
+    if (cudaMemsetAsync(dev + s, 0, sizeof(int), p->stream) != cudaSuccess) return -1;
+    *dptr = dev + s;
+    return s;
+  }
+  // after the counting kernel: start the read-back
+  int post(int s) {
+    if (!p->count_ev[s] &&
+        cudaEventCreateWithFlags(&p->count_ev[s], cudaEventDisableTiming) != cudaSuccess)
+      return DCORA_ERR_CUDA;
+    if (cudaMemcpyAsync(host + s, dev + s, sizeof(int), cudaMemcpyDeviceToHost, p->stream) !=
+            cudaSuccess ||
+        cudaEventRecord(p->count_ev[s], p->stream) != cudaSuccess)
+      return DCORA_ERR_CUDA;
+    return DCORA_OK;
+  }
+  int get(int s, int *out) {
+    if (cudaEventSynchronize(p->count_ev[s]) != cudaSuccess) return DCORA_ERR_CUDA;
+    *out = host[s];
+    return DCORA_OK;
+  }
+};
 
 // Riemannian Hessian-vector product at x1: out = proj(V*Q - V*sym(Y^T EG))
 // with_dot: also leaves <v, out> in partial slot 0
@@ -411,7 +435,6 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   double *t0 = p->vec(WS_T0), *xq = p->vec(WS_T1), *Heta = p->vec(WS_HETA);
   if (!x2 || !EG || !gf || !S || !eta || !delta || !Hd || !r || !z || !t0 || !xq || !Heta)
     return DCORA_ERR_ALLOC;
-  int *counters = p->flags + (size_t)NF * A;
   const auto tstart = std::chrono::steady_clock::now();
   DCORA_TRY(set_user_mask(p, active));
   // per-agent control kernels run over the caller's subset only
@@ -427,18 +450,18 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   // initial statistics: fInit, gradNormInit (QuadraticOptimizer.cpp:30-31)
   DCORA_TRY(eval_f(p, x1, xq, S_F1, F_USER));
   DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_USER, xq));
-  DCORA_TRY(zero_counter(p, 0));
+  CountRing ring(p);
   const int single_mode = prm->RTR_iterations == 1;
   const int max_outer = single_mode ? 12 : prm->RTR_iterations;
   const double Delta0 = prm->RTR_initial_radius;
+  int *dcnt = nullptr;
+  int outer_slot = ring.open(&dcnt);
+  if (outer_slot < 0) return DCORA_ERR_CUDA;
   rtr_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
                                             p->scal, prm->gradnorm_tol, Delta0,
-                                            single_mode ? Delta0 : 5.0 * Delta0,
-                                            counters);
+                                            single_mode ? Delta0 : 5.0 * Delta0, dcnt);
   DCORA_LAUNCH_CHECK(p);
-  int cnt[2];
-  DCORA_TRY(read_counters(p, cnt));
-  int n_outer = cnt[0];
+  DCORA_TRY(ring.post(outer_slot));
   pt.mark(0);
 
   if (prm->method == 1) {
@@ -451,10 +474,9 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     DCORA_TRY(launch_axpby(p, eta, -1, -prm->RGD_stepsize, g, -1, 0.0, nullptr, F_USER));
     DCORA_TRY(launch_retract(p, x1, eta, x2, prm->retraction, F_USER));
     DCORA_TRY(launch_copy(p, x1, x2, F_USER));
-    n_outer = 0;
   }
 
-  for (int it = 0; it < max_outer && n_outer > 0; ++it) {
+  for (int it = 0; it < max_outer && prm->method != 1; ++it) {
     // ---- tCG (SolversTR::tCG_TR), eta0 = 0
     // r = gf, eta = 0, Heta = 0.  H eta is accumulated with eta (H eta += c H delta, the
     // Hessian is linear on the tangent space), which saves the SpMM of a separate H*eta
@@ -464,28 +486,36 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     tcg_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(launch_axpby(p, delta, -1, -1.0, z, -1, 0.0, nullptr, F_TCG));
-    int n_tcg = n_outer;
+    // how many agents entered this outer iteration?  (counted by the kernel before the
+    // four launches above: if none did, they found every agent switched off)
+    int n_outer = 0;
+    DCORA_TRY(ring.get(outer_slot, &n_outer));
+    if (n_outer == 0) break;
     pt.mark(1);
     ++n_outer_done;
-    for (int j = 0; j < prm->RTR_tCG_iterations && n_tcg > 0; ++j) {
+    int prev_slot = -1;
+    for (int j = 0; j < prm->RTR_tCG_iterations; ++j) {
       DCORA_TRY(rhess(p, x1, S, delta, t0, Hd, F_TCG, true));  // + <delta, H delta>
       tcg_stepA_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
       // eta += c delta, Heta += c Hd, r += c_r Hd and <r, r> in one pass
       DCORA_TRY(launch_tcg_update(p, S_CETA, S_CR, delta, Hd, eta, Heta, r, F_STEP));
-      DCORA_TRY(zero_counter(p, 1));
+      const int slot = ring.open(&dcnt);
+      if (slot < 0) return DCORA_ERR_CUDA;
       tcg_stepB_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
-                                                 p->scal, j, 0, prm->RTR_tCG_iterations,
-                                                 counters);
+                                                 p->scal, j, 0, prm->RTR_tCG_iterations, dcnt);
       DCORA_LAUNCH_CHECK(p);
+      DCORA_TRY(ring.post(slot));
       pt.mark(2);
+      // the PREVIOUS iteration's count (this iteration's is still in flight): zero means
+      // the tCG of every agent had ended and the launches above exited at once
+      if (prev_slot >= 0) {
+        int n_tcg = 0;
+        DCORA_TRY(ring.get(prev_slot, &n_tcg));
+        if (n_tcg == 0) break;
+      }
       ++n_inner_done;
-      // how many agents go on?  Read before the preconditioner so that the last
-      // iteration (the usual case: tCG ends for every agent of the colour at once)
-      // does not launch a K5 / projection / stepC / update that would exit at once
-      DCORA_TRY(read_counters(p, cnt));
-      n_tcg = cnt[1];
-      if (n_tcg == 0) { pt.mark(3); break; }
+      prev_slot = slot;
       DCORA_TRY(launch_precond(p, x1, r, z, F_TCG, nullptr, 0, r));  // + <z, r>
       tcg_stepC_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal);
       DCORA_LAUNCH_CHECK(p);
@@ -506,16 +536,16 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     pt.mark(4);
     DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));
     DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT, xq));
-    DCORA_TRY(zero_counter(p, 0));
+    outer_slot = ring.open(&dcnt);
+    if (outer_slot < 0) return DCORA_ERR_CUDA;
     rtr_accept_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
-                                                max_outer, single_mode, counters);
+                                                max_outer, single_mode, dcnt);
     DCORA_LAUNCH_CHECK(p);
-    if (it + 1 < max_outer) {   // else the loop ends anyway (read_scalars syncs below)
-      DCORA_TRY(read_counters(p, cnt));
-      n_outer = cnt[0];
-    }
+    DCORA_TRY(ring.post(outer_slot));
     pt.mark(5);
     if (prm->time_bound_s > 0.0) {
+      // the reference's wall-clock bound is checked against finished work
+      DCORA_CUDA(cudaStreamSynchronize(p->stream));
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count();
       if (el > prm->time_bound_s) break;
     }

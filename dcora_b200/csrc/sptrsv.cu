@@ -14,7 +14,8 @@
 // its own pre-compiled TAPE: the factor values arrive in consumption order through a
 // per-warp shared-memory ring that is filled by bulk asynchronous copies (cp.async.bulk +
 // mbarrier, i.e. TMA) running ahead of the consumer and straight through the barriers;
-// only the gathers from the solution panels wait for a barrier.  The r right-hand sides
+// only the gathers from the solution panels wait for a barrier.  (The alternatives that were
+// measured are listed at the end of trsv_dev.cuh.)  The r right-hand sides
 // are processed together; the panels are (factor row, r) row-major, the same memory shape
 // as every other vector.
 #include <cstdlib>
@@ -67,23 +68,19 @@ trsv_tape_kernel(const int *__restrict__ flags, int mask_flag,
       (trace_buf && agent == trace_agent && gwarp == 0 && (threadIdx.x & 31) == 0) ? trace_buf
                                                                                    : nullptr;
   if (trace) *trace++ = globaltimer_ns();
+  if (trace && (dbg & 8)) {   // per-iteration cycle stamps of this warp, behind the slot stamps
+    rd.itrace = reinterpret_cast<long long *>(trace_buf) + 64;
+    rd.itrace_left = 120;
+  }
   // T[f] = V[column of factor row f]
   const long long f0 = arow0[agent], f1 = arow0[agent + 1];
   const int tid = crank * NTHREADS + threadIdx.x;
   constexpr int NT = CL * NTHREADS;
-  for (long long e = (long long)f0 * R + tid; e < f1 * R; e += NT) {
-    const long long f = e / R;
-    const int q = (int)(e - f * R);
-    T[e] = V[(size_t)frow_col[f] * R + q];
-  }
+  trsv_permute_rows<R, false>(f0, f1, tid, NT, frow_col, V, T);
   phase_sync<CL>();
   if (trace) *trace++ = globaltimer_ns();
-  trsv_run<R, DH, CL>(rd, T, X, trace);
-  for (long long e = (long long)f0 * R + tid; e < f1 * R; e += NT) {
-    const long long f = e / R;
-    const int q = (int)(e - f * R);
-    OUT[(size_t)frow_col[f] * R + q] = X[e];
-  }
+  trsv_run<R, DH, CL>(rd, T, X, (int)f0, trace);
+  trsv_permute_rows<R, true>(f0, f1, tid, NT, frow_col, X, OUT);
   if (trace) { *trace++ = globaltimer_ns(); *trace = 0ull; }
   rd.drain();
 }

@@ -31,12 +31,20 @@
 // A tape is a sequence of fixed-size RECORDS of 16 + 8 DH^2 8-byte words (doubles, or two
 // packed int32), one record per iteration of a round; the kernel moves one record per bulk
 // copy (TMA) into one slot of the warp's shared-memory ring:
-//   word 0..3    source rows c[0..7] of the 8 lane groups (two int32 per word)
+//   word 0..3    source rows of the record TAPE_AHEAD records further on (two int32 per
+//                word, one per lane group): the kernel gathers its panel rows that many
+//                iterations ahead and never has to wait for a future record to do so
 //   word 4       {niter, gpt | type << 8 | last_of_slot << 16}   (first record of a round)
-//   word 5..12   8 x { dst_row0 | -1, nrows }, one per lane group (first record of a round)
-//   word 13..15  padding
-//   word 16..    8 x DH x DH doubles [group][b][a]: lane (group, b) owns DH consecutive
-//                words = column b of its tile
+//   word 5..8    8 x int32 (dst_row0 << 3 | nrows), -1: none     (first record of a round)
+//   word 9       {records from this one to the end of its barrier slot, 0}   (first record of a round)
+//   word 10..11  padding
+//   word 12..15  the record's own source rows (host replay; unused by the kernel)
+//   word 16..    8 x DH x DH doubles, lane (group, b) owns column b of its tile.  DH = 4:
+//                [half][lane][2] -- rows 0,1 of every lane's column, then rows 2,3 -- so
+//                that each of the lane's two 128-bit shared loads is a conflict-free,
+//                contiguous 512 bytes per warp; DH = 3: [group][b][a]
+// Every tape starts with a round of TAPE_AHEAD zero records (they carry the source rows of
+// the first real records); it belongs to the first barrier slot.
 // A round = `niter` records executed by one warp: `gpt` adjacent groups share one task
 // (their partial sums are added at the end of the round).  A cluster barrier follows the
 // round flagged last_of_slot; every warp of the agent has exactly one such round per slot
@@ -49,7 +57,14 @@ namespace dcora {
 
 constexpr int TRSV_MAX_BLOCK = 512;   // larger ND blocks are split into a chain
 constexpr int TAPE_REC_HEADER = 16;   // words before the tile values of a record
+constexpr int TAPE_AHEAD = 4;         // records between a record and the one whose rows it names
+                                      // (= depth of the kernel's ring: its gather look-ahead)
 inline int tape_record_words(int dh) { return TAPE_REC_HEADER + 8 * dh * dh; }
+// word (behind the header) of tile element (row a, column b) of lane group g
+inline int tape_value_word(int dh, int g, int b, int a) {
+  if (dh == 4) return (a >> 1) * 64 + (g * 4 + b) * 2 + (a & 1);
+  return (g * dh + b) * dh + a;
+}
 
 enum TapeType : int { TAPE_FWD = 0, TAPE_MID = 1, TAPE_BWD = 2 };
 

@@ -76,7 +76,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 
 // Per-warp ring of RING_SLOTS tape records in shared memory, filled by bulk asynchronous
-// copies (TMA) that complete on one mbarrier per slot.  The tape is static data: record i
+// copies (TMA) that complete on one mbarrier per slot -- no LSU work at all for the tape,
+// which matters: with 16 warps per SM the kernel is bound by the LSU's wavefronts (panel
+// gathers + shared-memory reads), see the notes at the end of this file.  The tape is static data: record i
 // is requested as soon as record i - RING_SLOTS has been consumed, regardless of barriers,
 // and record i + L2_AHEAD is pulled into L2 at the same time, so that the ring's own
 // requests are L2 hits (8 records in flight alone would cap a warp's stream at
@@ -90,6 +92,8 @@ struct TapeRing {
   int issued, ready;              // record counters (warp-uniform)
   unsigned base;                  // records that went through these mbarriers before
   int dbg = 0;                    // experiment switches (DCORA_K5_DBG), 0 in production
+  long long *itrace = nullptr;    // per-iteration clock64 stamps of one warp (debug aid)
+  int itrace_left = 0;
 
   __device__ __forceinline__ void setup(unsigned long long *ring_, unsigned long long *mbar_) {
     ring = ring_;
@@ -189,40 +193,63 @@ struct TapeRing {
   }
 };
 
+// per-iteration cycle stamps of one warp (tools/trsv_trace.py with DCORA_K5_DBG=8): compiled
+// in only with -DDCORA_K5_TRACE_ITERATIONS (the four tests per record cost ~10 %)
+#ifdef DCORA_K5_TRACE_ITERATIONS
+#define DCORA_K5_STAMP() \
+  do { if (rd.itrace && rd.itrace_left > 0) *rd.itrace++ = clock64(); } while (0)
+#define DCORA_K5_STAMP_END() \
+  do { if (rd.itrace && rd.itrace_left > 0) { *rd.itrace++ = clock64(); --rd.itrace_left; } } while (0)
+#else
+#define DCORA_K5_STAMP() do {} while (0)
+#define DCORA_K5_STAMP_END() do {} while (0)
+#endif
+
+__device__ __forceinline__ unsigned lds32(uint32_t addr) {
+  unsigned v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 // Executes every round of one warp's tape (format: trsv.h).  Lane (g, a) of the warp --
-// group g = lane / 4, a = lane % 4 -- owns COLUMN a of its group's tile: per iteration it
+// group g = lane / 4, a = lane % 4 -- owns COLUMN a of its group's tile: per record it
 // needs one row of the source panel (R doubles) and DH tape words, and accumulates all DH
 // rows of the product; the 4 lanes of a group (and the `gpt` groups of a task) are summed
 // once per round.  A cluster barrier follows the last round of every slot.
 template <int R, int DH, int CL>
 __device__ __forceinline__ void trsv_run(TapeRing<TapeRec<DH>::W> &rd, double *T, double *X,
-                                         unsigned long long *&trace) {
-  // The source rows are gathered from L2 PFD iterations ahead of their use (register ring,
-  // statically indexed by unrolling): 3 deep for r <= 8, 1 deep for higher ranks.
+                                         int row0, unsigned long long *&trace) {
+  static_assert(TAPE_AHEAD == 4, "the row window below holds TAPE_AHEAD rows");
+  // The source rows are gathered from L2 PFD records ahead of their use (register ring,
+  // statically indexed by unrolling).  Which rows: every record names the rows of the
+  // record TAPE_AHEAD further on, so the window (w0..w3) always holds the rows of the
+  // current and the next three records and no future record has to have landed for a gather
+  // to be issued.
   constexpr int PFD = R <= 8 ? 3 : 1;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, a = lane & 3;
-  uint32_t cw_off = (uint32_t)(g >> 1) * 8;
-  uint32_t c_shift = (g & 1) ? 32u : 0u;
-  uint32_t m_off = (uint32_t)(TAPE_REC_HEADER + (g * DH + a) * DH) * 8;
+  uint32_t cw_off = (uint32_t)g * 4;
+  uint32_t m_off = DH == 4 ? (uint32_t)(TAPE_REC_HEADER + lane * 2) * 8
+                           : (uint32_t)(TAPE_REC_HEADER + (g * DH + a) * DH) * 8;
   // keep the lane constants in registers (the compiler would otherwise rebuild them from
   // the thread index -- a slow special-register read -- inside the loop)
-  asm volatile("" : "+r"(cw_off), "+r"(c_shift), "+r"(m_off));
+  asm volatile("" : "+r"(cw_off), "+r"(m_off));
   const int nrec = rd.nrec;
+  int w0 = row0 + a, w1 = w0, w2 = w0, w3 = w0;
   int rec = 0;
   while (rec < nrec) {
     rd.wait(rec);
     const uint32_t hs = rd.rec_s(rec);
     const unsigned long long ctl = lds64(hs + 4 * 8);
-    const unsigned long long d0 = lds64(hs + (5 + g) * 8);
+    const int dpk = (int)lds32(hs + 5 * 8 + cw_off);
     const int niter = lo32(ctl), cw = hi32(ctl);
     const int gpt = cw & 0xff, type = (cw >> 8) & 0xff;
     const bool last_of_slot = (cw >> 16) & 1;
-    const int r0 = lo32(d0), nrows = hi32(d0);
+    const int r0 = dpk >> 3, nrows = dpk & 7;
     const double *src = type == TAPE_BWD ? X : T;
     double *dst = type == TAPE_FWD ? T : X;
     const bool accumulate = type != TAPE_MID;
-    const bool writer = r0 >= 0 && a < nrows && (g & (gpt - 1)) == 0;
+    const bool writer = dpk >= 0 && a < nrows && (g & (gpt - 1)) == 0;
     const size_t o = (size_t)(r0 + a) * R;
     // the destination's current value (accumulating tasks): independent of everything
     // below, so its latency hides behind the loop
@@ -243,11 +270,6 @@ __device__ __forceinline__ void trsv_run(TapeRing<TapeRec<DH>::W> &rd, double *T
     for (int s2 = 0; s2 < PFD; ++s2)
 #pragma unroll
       for (int q = 0; q < R; ++q) yq[s2][q] = 0.0;
-    // source row of this lane's group in (ready) record ri
-    auto src_row = [&](int ri) {
-      const unsigned long long cwd = lds64(rd.rec_s(ri) + cw_off);
-      return (int)(unsigned)(cwd >> c_shift) + a;
-    };
     auto gather = [&](int row, double (&dstv)[R]) {
       if (a < DH && !(rd.dbg & 1)) {
         const double *yj = src + (size_t)row * R;
@@ -256,24 +278,26 @@ __device__ __forceinline__ void trsv_run(TapeRing<TapeRec<DH>::W> &rd, double *T
       }
     };
     const int last = rec + niter - 1;
-#pragma unroll
-    for (int s2 = 0; s2 < PFD; ++s2)
-      if (s2 < niter) { rd.wait(rec + s2); gather(src_row(rec + s2), yq[s2]); }
-    // the barrier of the next look-ahead record is probed one iteration early
-    uint32_t ok = (rec + PFD <= last) ? rd.probe(rec + PFD) : 0u;
+    if (niter > 0) gather(w0, yq[0]);
+    if constexpr (PFD > 1) { if (niter > 1) gather(w1, yq[1]); }
+    if constexpr (PFD > 2) { if (niter > 2) gather(w2, yq[2]); }
+    // the barrier of the next record is probed one iteration early
+    uint32_t ok = rec < last ? rd.probe(rec + 1) : 0u;
     for (int it0 = 0; it0 < niter; it0 += PFD) {
 #pragma unroll
       for (int u = 0; u < PFD; ++u) {
         const int ri = rec + it0 + u;
         if (ri <= last) {
-          const bool more = ri + PFD <= last;
-          int nrow = 0;
-          if (more) { rd.confirm(ri + PFD, ok); nrow = src_row(ri + PFD); }
-          const uint32_t ms = rd.rec_s(ri) + m_off;
+          DCORA_K5_STAMP();
+          if (ri > rec) rd.confirm(ri, ok);
+          DCORA_K5_STAMP();
+          const uint32_t rs = rd.rec_s(ri);
+          const int w4 = (int)lds32(rs + cw_off) + a;   // row of record ri + TAPE_AHEAD
+          const uint32_t ms = rs + m_off;
           double m[DH];
           if (a < DH) {
             if constexpr (DH == 4) {
-              const double2 m01 = lds_f64x2(ms), m23 = lds_f64x2(ms + 16);
+              const double2 m01 = lds_f64x2(ms), m23 = lds_f64x2(ms + 512);
               m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
             } else {
 #pragma unroll
@@ -283,13 +307,16 @@ __device__ __forceinline__ void trsv_run(TapeRing<TapeRec<DH>::W> &rd, double *T
 #pragma unroll
             for (int i = 0; i < DH; ++i) m[i] = 0.0;
           }
-          if (ri + PFD + 1 <= last) ok = rd.probe(ri + PFD + 1);
+          if (ri < last) ok = rd.probe(ri + 1);
 #pragma unroll
           for (int i = 0; i < DH; ++i)
 #pragma unroll
             for (int q = 0; q < R; ++q) acc[i][q] = fma(m[i], yq[u][q], acc[i][q]);
-          if (more) gather(nrow, yq[u]);
+          DCORA_K5_STAMP();
+          if (ri + PFD <= last) gather(PFD == 3 ? w3 : PFD == 2 ? w2 : w1, yq[u]);
+          w0 = w1; w1 = w2; w2 = w3; w3 = w4;
           rd.refill();
+          DCORA_K5_STAMP_END();
         }
       }
     }
@@ -333,6 +360,44 @@ __device__ __forceinline__ void trsv_run(TapeRing<TapeRec<DH>::W> &rd, double *T
     }
   }
 }
+
+// T[f] = V[column of factor row f] for the agent's factor rows [f0, f1), dealt to `nt`
+// threads; the reverse with TO_COLS (OUT[column] = X[f]).  Row-wise: one index load and R
+// independent element moves per row.
+template <int R, bool TO_COLS>
+__device__ __forceinline__ void trsv_permute_rows(long long f0, long long f1, int tid, int nt,
+                                                  const int *__restrict__ frow_col,
+                                                  const double *in, double *out) {
+  for (long long f = f0 + tid; f < f1; f += nt) {
+    const size_t c = (size_t)frow_col[f] * R, ff = (size_t)f * R;
+    double v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = in[(TO_COLS ? ff : c) + q];
+#pragma unroll
+    for (int q = 0; q < R; ++q) out[(TO_COLS ? c : ff) + q] = v[q];
+  }
+}
+
+// ---- What bounds this kernel (B200, config-5 agent: 16810 rows, 2 x 1.4 M tile values, 25
+// barrier slots, 64 warps = 4 CTAs x 16 warps; per-iteration clock64 stamps, DCORA_K5_DBG=8;
+// ncu source view; SASS control words) -----------------------------------------------------
+//  * ~1000 cycles per record and warp in every variant tried, i.e. ~65 cycles of some
+//    SM-wide resource per warp-iteration: the LSU.  A record costs 5 scattered 8-byte panel
+//    gathers (8 lane groups x 160 bytes: 8-16 wavefronts each), the shared-memory reads of
+//    the tile column, and -- when the tape or the gathers are staged through shared memory
+//    with cp.async -- their write side too.
+//  * register prefetch of the panel rows PFD records ahead is defeated by the compiler: all
+//    in-flight gathers share ONE scoreboard (decoded control words: every gather `wr 5`, the
+//    first DFMA of an iteration waits on SB5), so it waits for the newest gather.
+//  * variants measured (one agent alone / its colour class of 28, microseconds per solve):
+//      TMA ring, records name their own rows (look-ahead wait on future records)  243 / 281
+//      TMA ring, rows named TAPE_AHEAD records ahead (this file)                   256 / 282
+//      cp.async ring for the tape, register gathers                               286 / 307
+//      cp.async for tape and panel rows (commit groups, no scoreboard aliasing)   388 / 393
+//      ... the same with sector-coalesced gathers + conflict-free tile layout     345 / 353
+//    i.e. every byte moved through the LSU a second time costs more than the stall it removes.
+//  * switching the gathers off entirely (DCORA_K5_DBG=1) gives 207 / 236; the bulk L2 prefetch
+//    changes nothing (the ring's own requests already hide HBM).
 
 }  // namespace
 }  // namespace dcora

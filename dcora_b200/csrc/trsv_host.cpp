@@ -184,6 +184,21 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
   out->nwarps = nwarps_total;
   out->dh = dh;
   out->warp_tape.assign(nwarps_total, std::vector<uint64_t>());
+  {
+    // every tape starts with a round of TAPE_AHEAD zero records
+    const int recw0 = tape_record_words(dh);
+    for (std::vector<uint64_t> &tp : out->warp_tape) {
+      tp.assign((size_t)TAPE_AHEAD * recw0, 0);
+      for (int it = 0; it < TAPE_AHEAD; ++it) {
+        uint64_t *rec = &tp[(size_t)it * recw0];
+        for (int w = 0; w < 4; ++w) rec[12 + w] = pack2(row_offset, row_offset);
+        if (it == 0) {
+          rec[4] = pack2(TAPE_AHEAD, 1 | (TAPE_FWD << 8));
+          for (int w = 0; w < 4; ++w) rec[5 + w] = pack2(-1, -1);
+        }
+      }
+    }
+  }
   out->stored_values = 0;
   out->crit_iters = out->crit_rounds = out->ideal_iters = 0;
   out->nslots = 0;
@@ -479,26 +494,26 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
             if (q < tk.ntiles()) { c[g] = R0 + tk.src[q]; vp[g] = &tk.val[(size_t)q * bs]; }
           }
         }
-        for (int g = 0; g < 8; g += 2) rec[g / 2] = pack2(c[g], c[g + 1]);
+        for (int g = 0; g < 8; g += 2) rec[12 + g / 2] = pack2(c[g], c[g + 1]);
         if (it == 0) {
           rec[4] = pack2(niter, gpt | (type << 8) | ((last ? 1 : 0) << 16));
+          int dpk[8];
           for (int g = 0; g < 8; ++g) {
             const int ti = g / gpt;
+            dpk[g] = -1;
             if (rd && ti < (int)rd->tasks.size()) {
               const Task &tk = tasks[rd->tasks[ti]];
-              rec[5 + g] = pack2(R0 + tk.r0, tk.nrows);
-            } else {
-              rec[5 + g] = pack2(-1, 0);
+              dpk[g] = ((R0 + tk.r0) << 3) | tk.nrows;
             }
           }
+          for (int g = 0; g < 8; g += 2) rec[5 + g / 2] = pack2(dpk[g], dpk[g + 1]);
         }
-        // lane (group g, column bb) owns DH consecutive words: its column of the
-        // tile, rows 0..DH-1 (for DH = 4: two 128-bit shared loads per iteration)
+        // lane (group g, column bb) owns column bb of its tile, rows 0..DH-1
         uint64_t *v = rec + TAPE_REC_HEADER;
         for (int g = 0; g < 8; ++g)
           for (int bb = 0; bb < dh; ++bb)
             for (int a = 0; a < dh; ++a)
-              *v++ = dbits(vp[g] ? vp[g][a * dh + bb] : 0.0);
+              v[tape_value_word(dh, g, bb, a)] = dbits(vp[g] ? vp[g][a * dh + bb] : 0.0);
         if (rd) out->stored_values += 8 * bs;
       }
     };
@@ -519,6 +534,29 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
             k, nb, Lf, Lb, out->nslots, (long long)out->crit_iters, (long long)out->ideal_iters,
             (long long)out->crit_rounds, (long long)out->stored_values,
             2 * (long long)F.Lx.size());
+  // words 0..3 of record j <- own source rows (words 12..15) of record j + TAPE_AHEAD;
+  // word 9 of every round's first record <- records left in its barrier slot
+  {
+    const int recw = tape_record_words(dh);
+    for (std::vector<uint64_t> &tp : out->warp_tape) {
+      const size_t n = tp.size() / recw;
+      for (size_t j = 0; j < n; ++j)
+        for (int w = 0; w < 4; ++w)
+          tp[j * recw + w] = j + TAPE_AHEAD < n ? tp[(j + TAPE_AHEAD) * recw + 12 + w]
+                                                : pack2(row_offset, row_offset);
+      std::vector<size_t> firsts;   // first records of the rounds of the current slot
+      for (size_t j = 0; j < n;) {
+        const int niter = lo32(tp[j * recw + 4]);
+        const bool last = ((hi32(tp[j * recw + 4]) >> 16) & 1) != 0;
+        firsts.push_back(j);
+        j += (size_t)niter;
+        if (last) {
+          for (size_t f : firsts) tp[f * recw + 9] = pack2((int)(j - f), 0);
+          firsts.clear();
+        }
+      }
+    }
+  }
   return DCORA_OK;
 }
 
@@ -529,7 +567,7 @@ void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offs
   const int dh = S.dh, nw = S.nwarps, R0 = row_offset;
   for (int f = 0; f < S.k; ++f) T[R0 + f] = b[F.perm[f]];
   const int recw = tape_record_words(dh);
-  std::vector<size_t> pos(nw, 0);
+  std::vector<size_t> pos(nw, (size_t)TAPE_AHEAD * recw);   // past the zero round
   for (int sl = 0; sl < S.nslots; ++sl) {
     for (int wi = 0; wi < nw; ++wi) {
       const std::vector<uint64_t> &tp = S.warp_tape[wi];
@@ -540,7 +578,11 @@ void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offs
         const int gpt = cw & 0xff, type = (cw >> 8) & 0xff;
         last = ((cw >> 16) & 1) != 0;
         int r0[8], nrows[8];
-        for (int g = 0; g < 8; ++g) { r0[g] = lo32(h[5 + g]); nrows[g] = hi32(h[5 + g]); }
+        for (int g = 0; g < 8; ++g) {
+          const int d = (g & 1) ? hi32(h[5 + g / 2]) : lo32(h[5 + g / 2]);
+          r0[g] = d >> 3;
+          nrows[g] = d < 0 ? 0 : (d & 7);
+        }
         const double *src = type == TAPE_BWD ? X : T;
         double *dst = type == TAPE_FWD ? T : X;
         const bool accumulate = type != TAPE_MID;
@@ -548,12 +590,12 @@ void agent_tape_apply_host(const AgentTape &S, const HostFactor &F, int row_offs
         for (int it = 0; it < niter; ++it) {
           const uint64_t *rec = &tp[p];
           int c[8];
-          for (int g = 0; g < 8; g += 2) { c[g] = lo32(rec[g / 2]); c[g + 1] = hi32(rec[g / 2]); }
+          for (int g = 0; g < 8; g += 2) { c[g] = lo32(rec[12 + g / 2]); c[g + 1] = hi32(rec[12 + g / 2]); }
           const uint64_t *v = rec + TAPE_REC_HEADER;
           for (int g = 0; g < 8; ++g)
             for (int a = 0; a < dh; ++a)
               for (int bb = 0; bb < dh; ++bb)
-                acc[g * 4 + a] += bitsd(v[(size_t)(g * dh + bb) * dh + a]) * src[c[g] + bb];
+                acc[g * 4 + a] += bitsd(v[tape_value_word(dh, g, bb, a)]) * src[c[g] + bb];
           p += recw;
         }
         for (int g = 0; g < 8; g += gpt) {

@@ -188,6 +188,8 @@ class RBCD:
             self.H = torch.zeros((world * plan.seg_cols, r), dtype=torch.float64, device=self.device)
             self.sendbuf = torch.zeros((plan.seg_cols, r), dtype=torch.float64, device=self.device)
         self.agent_updates = 0
+        self.inner_iterations = 0      # tCG iterations summed over the agent updates
+        self.outer_iterations = 0
         # RBCD++ (Nesterov acceleration, Agent.cpp:535-596,1158-1214; AgentParameters
         # acceleration / restartInterval, Agent.h:40-185)
         self.acc = bool(acceleration)
@@ -216,6 +218,26 @@ class RBCD:
             self.alpha = 0.0
         else:
             self.P.set_iterate_tracking(True)   # forget the tracked copy
+
+    def _count(self, active):
+        """Bookkeeping of an optimize() call over the agents in `active`."""
+        from ._lib import ROPT_RESULT_DTYPE
+        res = np.frombuffer(self.opt._raw, dtype=ROPT_RESULT_DTYPE)
+        m = active.astype(bool)
+        self.agent_updates += int(m.sum())
+        self.inner_iterations += int(res["inner_iterations"][m].sum())
+        self.outer_iterations += int(res["outer_iterations"][m].sum())
+
+    def load_host_X(self, X_host):
+        """Upload the local iterate from a host buffer (numpy (r, K_local), column-major,
+        ideally pinned) into the device buffer the solver works on."""
+        if getattr(self, "X", None) is None:
+            self.X = self.torch.empty((self.plan.K, self.r), dtype=self.torch.float64, device=self.device)
+        self.P.load_iterate(X_host, self.X)
+        self.set_device_X(self.X)
+
+    def store_host_X(self, X_host):
+        self.P.store_iterate(self.X, X_host)
 
     def get_X(self):
         """numpy (r, K_local)."""
@@ -249,7 +271,7 @@ class RBCD:
         if active.any():
             self.P.update_G(self.X, self.H, active)
             self.X = self.opt.optimize(self.X, active, out=self.X)
-            self.agent_updates += int(active.sum())
+            self._count(active)
 
     def _accelerated_step(self, active):
         """One driver iteration of RBCD++ (Agent.cpp:535-596).  The non-selected agents run
@@ -272,7 +294,7 @@ class RBCD:
             if active.any():
                 self.P.update_G(Xprev, self.H, active)
                 Xr = self.opt.optimize(Xprev, active, out=Xr)
-                self.agent_updates += int(active.sum())
+                self._count(active)
             self.X, self.V, self.Y = Xr, Xr.clone(), Xr.clone()
             self.gamma = 0.0
             self.alpha = 0.0
@@ -284,7 +306,7 @@ class RBCD:
         if active.any():
             self.P.update_G(Y, self.H, active)
             Xn = self.opt.optimize(Y, active, out=Xn)
-            self.agent_updates += int(active.sum())
+            self._count(active)
         # updateV: V = projectToManifold(V + gamma (X - Y))
         V = self.P.combine_project(1.0, self.V, self.gamma, Xn - Y, None)
         self.X, self.V, self.Y = Xn, V, Y

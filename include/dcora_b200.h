@@ -257,6 +257,15 @@ int dcora_problem_pack_columns(dcora_problem *p, const double *X,
  * written to the buffer itself.  Needs a registered coupling; off by default. */
 int dcora_problem_set_iterate_tracking(dcora_problem *p, int32_t on);
 
+/* Moving the device-resident iterate in and out: a driver whose Agent::X lives in host
+ * memory between RBCD iterations (setX / getX, include/DCORA/Agent.h:583,596) uploads it
+ * once per iteration into its device buffer and reads the result back once.  Both are
+ * r x K column-major doubles in the reference ordering; the copies run on the handle's
+ * stream and are complete on return.  load also forgets any tracked pointer (the buffer's
+ * content changed). */
+int dcora_problem_load_iterate(dcora_problem *p, const double *X_host, double *X_device);
+int dcora_problem_store_iterate(dcora_problem *p, const double *X_device, double *X_host);
+
 /* Per-agent 0.5 <X Q, X> and <X, G>: the global cost of the partitioned
  * problem is sum_a quad_a + 0.5 lin_a (cross terms appear in two agents). */
 int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,

@@ -30,7 +30,7 @@ def main():
     meas, gt, idx = synthetic.grid3d(a.grid, 0.1, seed=0)
     gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, a.agents))
     S = rbcd.RBCD(gp, a.rank, rank=0, world=1, device=0, params=dc.ROptParameters(time_bound_s=0.0))
-    n = 256
+    n = 1024
     alone = np.zeros(a.agents, np.uint8)
     colour = (S.local_colors == S.local_colors[a.agent]).astype(np.uint8)
     for name, act in (("alone", alone), (f"its colour class ({int(colour.sum())} agents)", colour),
@@ -39,6 +39,8 @@ def main():
         ptr = act.ctypes.data_as(_lib.c_uint8_p) if act is not None else None
         _lib.check(lib.dcora_debug_trsv_trace(S.P.h, a.agent, ptr, st, n))
         t = np.array(list(st), dtype=np.uint64)
+        it = t[64:64 + 480].astype(np.int64)
+        t = t[:64]
         end = int(np.argmax(t[1:] == 0)) + 1
         t = t[:end].astype(np.int64)
         dt = np.diff(t) / 1e3
@@ -46,6 +48,13 @@ def main():
               f"{len(dt) - 2} slots")
         print(f"  rhs load {dt[0]:.1f} | slots " + " ".join(f"{d:.1f}" for d in dt[1:-1]) +
               f" | write-back {dt[-1]:.1f}")
+        if it[0] != 0:
+            q = it[:480].reshape(-1, 4)
+            q = q[q[:, 0] != 0]
+            print("  iterations of warp 0 (cycles): wait | loads+fma | refill | gap to next")
+            for k in range(min(len(q), 60)):
+                gap = q[k + 1, 0] - q[k, 3] if k + 1 < len(q) else 0
+                print(f"   {q[k,1]-q[k,0]:6d} {q[k,2]-q[k,1]:6d} {q[k,3]-q[k,2]:6d} {gap:6d}")
 
 
 if __name__ == "__main__":
