@@ -94,18 +94,30 @@ SYMBOLS = {
                                               C.c_double, C.c_int32, C.c_int32, VP]),
     "dcora_problem_set_coupling": (C.c_int, [VP, C.POINTER(HaloSegment), C.c_int32,
                                              c_int32_p, c_int32_p, c_double_p]),
+    "dcora_problem_set_coupling_keyed": (C.c_int, [VP, C.POINTER(HaloSegment), C.c_int32,
+                                                   c_int32_p, c_int32_p, c_double_p,
+                                                   C.POINTER(C.c_int64)]),
     "dcora_problem_halo_dim": (C.c_int64, [VP]),
     "dcora_problem_update_G": (C.c_int, [VP, VP, VP, c_uint8_p]),
     "dcora_problem_pack_columns": (C.c_int, [VP, VP, c_int32_p, C.c_int64, VP]),
     "dcora_problem_set_iterate_tracking": (C.c_int, [VP, C.c_int32]),
     "dcora_problem_load_iterate": (C.c_int, [VP, VP, VP]),
     "dcora_problem_store_iterate": (C.c_int, [VP, VP, VP]),
+    "dcora_project_to_rotation_group": (C.c_int, [c_double_p, C.c_int32, c_double_p]),
+    "dcora_problem_round_solution": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_align_trajectory": (C.c_int, [VP, VP, c_double_p, C.c_int32, VP]),
     "dcora_problem_cost_terms": (C.c_int, [VP, VP, c_double_p, c_double_p]),
     "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
                                                 c_uint8_p, VP]),
+    "dcora_problem_combine": (C.c_int, [VP, C.c_double, VP, C.c_double, VP, VP]),
     "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
     "dcora_problem_time_kernel": (C.c_int, [VP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "dcora_debug_trsv_trace": (C.c_int, [VP, C.c_int32, c_uint8_p, C.POINTER(C.c_uint64), C.c_int32]),
+    "dcora_selfcheck_coupling": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.POINTER(HaloSegment), C.c_int32,
+                                           c_int32_p, c_int32_p, c_double_p,
+                                           C.POINTER(C.c_int64), c_double_p,
+                                           C.POINTER(C.c_int64)]),
     "dcora_selfcheck_layout": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, c_double_p]),
     "dcora_selfcheck_cholesky": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,

@@ -21,6 +21,8 @@ import numpy as np
 from . import _lib
 from ._lib import AgentDesc, CertifyResult, HaloSegment, ROptParams, ROptResult, check
 
+C_int64_p = C.POINTER(C.c_int64)
+
 ORDER_SE, ORDER_RA = 0, 1
 RETRACT_QF, RETRACT_POLAR = 0, 1
 TCG_STATUS = ["TR_NEGCURVTURE", "TR_EXCREGION", "TR_LCON", "TR_SCON", "TR_MAXITER"]
@@ -118,6 +120,17 @@ def _new_out(like, r, K):
         import torch
         return torch.empty((K, r), dtype=torch.float64, device=like.device)
     return np.empty((r, K), dtype=np.float64, order="F")
+
+
+def project_to_rotation_group(M):
+    """projectToRotationGroup (src/DCORA_utils.cpp:1661-1675), d = 2 or 3."""
+    a = np.asfortranarray(np.asarray(M, dtype=np.float64))
+    d = a.shape[0]
+    assert a.shape == (d, d)
+    out = np.empty((d, d), order="F")
+    check(_lib.load().dcora_project_to_rotation_group(
+        a.ctypes.data_as(C.POINTER(C.c_double)), d, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
 
 
 class QuadraticProblem:
@@ -307,9 +320,10 @@ class QuadraticProblem:
         return res, v
 
     # -- multi-agent RBCD (Agent.cpp:113-152,844-906,1202-1278; Graph.cpp:685-822)
-    def set_coupling(self, C, halo_segments=()):
+    def set_coupling(self, C, halo_segments=(), row_key=None):
         """Register the cross-agent coupling: C is a scipy CSR (or (rowptr, col,
-        val)) of shape (K + KH, K); halo_segments = [(n, l, b), ...]."""
+        val)) of shape (K + KH, K); halo_segments = [(n, l, b), ...]; row_key (K + KH int64,
+        optional): accumulation order of the sources (dcora_problem_set_coupling_keyed)."""
         if isinstance(C, tuple):
             rowptr, col, val = C
         else:
@@ -324,9 +338,14 @@ class QuadraticProblem:
             segs[i].n, segs[i].l, segs[i].b = n, l, b
             KH += (self.d + 1) * n + l + b
         assert len(rowptr) == self.K + KH + 1, "coupling has the wrong number of rows"
-        check(self.lib.dcora_problem_set_coupling(
+        key = None
+        if row_key is not None:
+            key = np.ascontiguousarray(row_key, dtype=np.int64)
+            assert key.shape == (self.K + KH,)
+        check(self.lib.dcora_problem_set_coupling_keyed(
             self.h, segs, len(halo_segments), rowptr.ctypes.data_as(_lib.c_int32_p),
-            col.ctypes.data_as(_lib.c_int32_p), val.ctypes.data_as(_lib.c_double_p)))
+            col.ctypes.data_as(_lib.c_int32_p), val.ctypes.data_as(_lib.c_double_p),
+            key.ctypes.data_as(C_int64_p) if key is not None else None))
         self.KH = KH
 
     def _mask(self, active):
@@ -369,6 +388,26 @@ class QuadraticProblem:
         assert a.dtype == np.float64 and a.shape == (self.r, self.K) and a.flags.f_contiguous
         d = _Arg(X_device, self.r, self.K)
         check(self.lib.dcora_problem_store_iterate(self.h, d.ptr, a.ctypes.data_as(C.c_void_p)))
+
+    def round_solution(self, X):
+        """projectSolutionRASLAM (src/DCORA_utils.cpp:1984-2031) of the
+        whole batch as one solution: (r, K) -> (d, K)."""
+        a = _Arg(X, self.r, self.K)
+        out = _new_out(X, self.d, self.K)
+        o = _Arg(out, self.d, self.K, out=True)
+        check(self.lib.dcora_problem_round_solution(self.h, a.ptr, o.ptr))
+        return out
+
+    def align_trajectory(self, X, Tw0, is_global=True):
+        """alignLiftedTrajectoryToFrame (src/DCORA_utils.cpp:2262-2289); Tw0: (r, d+1)."""
+        a = _Arg(X, self.r, self.K)
+        T = np.asfortranarray(np.asarray(Tw0, dtype=np.float64))
+        assert T.shape == (self.r, self.d + 1)
+        out = _new_out(X, self.d, self.K)
+        o = _Arg(out, self.d, self.K, out=True)
+        check(self.lib.dcora_problem_align_trajectory(
+            self.h, a.ptr, T.ctypes.data_as(C.POINTER(C.c_double)), int(bool(is_global)), o.ptr))
+        return out
 
     def cost_terms(self, X):
         a = _Arg(X, self.r, self.K)

@@ -13,7 +13,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdcora_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["layout.cpp", "chol.cpp", "trsv_host.cpp", "selfcheck.cpp", "kernels.cu", "sptrsv.cu", "problem.cu",
-           "solver.cu", "rtr_cluster.cu", "certify.cu", "rbcd.cu"]
+           "solver.cu", "rtr_cluster.cu", "certify.cu", "rbcd.cu", "rounding.cu"]
 # (source, extra flags, object tag): the per-agent RTR cluster kernel, one translation unit per rank
 VARIANTS = [("rtr_cluster_inst.cu", [f"-DDCORA_CLUSTER_R={r}"], f"r{r}") for r in range(2, 9)]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -81,11 +81,17 @@ def build_examples(verbose=False):
     for src in sources:
         name = os.path.basename(src)
         exe = os.path.join(EXAMPLE_BIN, name[:-4])
-        deps = [src, os.path.join(inc, "dcora_b200.h"), os.path.join(inc, "dcora_b200", "DCORA.hpp")]
+        deps = [src, os.path.join(inc, "dcora_b200.h"), os.path.join(inc, "dcora_b200", "DCORA.hpp"),
+                os.path.join(inc, "dcora_b200", "DCORA_dist.hpp")]
         if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
             cmd = [CXX, "-std=c++17", "-O2", "-Wall", "-I", inc, src, "-L", HERE, "-ldcora_b200",
                    "-Wl,-rpath,$ORIGIN/../../dcora_b200", "-Wl,-rpath,/usr/local/cuda/lib64",
                    "-o", exe]
+            with open(src) as fh:
+                if "DCORA_dist.hpp" in fh.read():
+                    # the multi-process host links the CUDA runtime and NCCL directly
+                    cmd += ["-I", "/usr/local/cuda/include", "-L", "/usr/local/cuda/lib64",
+                            "-lcudart", "-lnccl"]
             subprocess.run(cmd, check=True)
         out.append(exe)
         if verbose:

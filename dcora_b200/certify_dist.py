@@ -37,6 +37,8 @@ class DistCertificate:
     iterations: int
     products: int          # block products S V (each = r matrix-vector products)
     converged: bool
+    theta: float = 0.0     # v^T S v of the returned direction (fastVerification's theta)
+    v: object = None       # local rows of the unit eigenvector estimate (device tensor, K_local)
 
 
 def _local_indices(S):
@@ -197,8 +199,14 @@ def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
             Hx = gram(Bx, times_S_cols(Bx))
             mu = float(t.linalg.eigvalsh(0.5 * (Hx + Hx.T))[0])
             lam = min(lam, mu)
+        # the escape direction: the smallest Ritz vector of the random-start iteration
+        v = Xr[:, 0].contiguous()
+        v = v / allsum((v * v).sum().reshape(1)).sqrt()
+        Vp = t.zeros((K, r), dtype=f64, device=dev)
+        Vp[:, 0] = v
+        theta = float(allsum((times_S(Vp)[:, 0] * v).sum().reshape(1)))
         return DistCertificate(is_psd=(lam + eta > 0.0), lambda_min=lam, residual=resid,
-                               iterations=it, products=nprod, converged=conv)
+                               iterations=it, products=nprod, converged=conv, theta=theta, v=v)
     finally:
         # restore the linear term of the RBCD state and re-arm the tracking
         S.exchange()

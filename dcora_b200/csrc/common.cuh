@@ -19,6 +19,11 @@ constexpr int NUM_SMS = 148;      // B200
 constexpr int DCORA_COUNT_RING = 8;  // slots of the solver's lagged "agents still iterating" counts
 
 void set_error(const std::string &msg);
+// Host threads of the set-up code (layout conversion, factorisation, tapes): the machine's
+// cores divided by the ranks on this node (LOCAL_WORLD_SIZE), NOT OMP_NUM_THREADS -- torchrun
+// exports OMP_NUM_THREADS=1, which would serialise the per-agent factorisations.  Override
+// with DCORA_SETUP_THREADS.
+int setup_threads();
 
 #define DCORA_CUDA(call)                                                        \
   do {                                                                          \
@@ -89,7 +94,7 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
                           const std::vector<int> &n, const std::vector<int> &l,
                           const std::vector<int> &poff, const dcora_halo_segment *segs,
                           int nseg, const int64_t *rowptr, const int32_t *col,
-                          const double *val, HostCoupling *out);
+                          const double *val, const int64_t *row_key, HostCoupling *out);
 
 // Device copy of the coupling (rbcd.cu).
 struct DeviceCoupling {

@@ -18,11 +18,26 @@
 // Both store Q^T (output-column major) so that Y = X*Q is reproduced with the
 // reference's own pairing of operands even if Q is only symmetric to rounding.
 #include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace dcora {
+
+int setup_threads() {
+  if (const char *e = std::getenv("DCORA_SETUP_THREADS")) {
+    const int v = std::atoi(e);
+    if (v > 0) return v;
+  }
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  int local = 1;
+  if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) local = std::max(1, std::atoi(e));
+  return std::max(1, hw / local);
+}
+
 
 static inline int ref_to_internal(int c, int d, int n, int l, int order) {
   if (order == DCORA_ORDER_SE) return c;
@@ -156,7 +171,7 @@ int build_layout(const dcora_agent_desc *agents, int A, int r, int d, int order,
     return DCORA_ERR_ARG;
   }
   std::vector<AgentLayout> AL(A);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(setup_threads())
   for (int a = 0; a < A; ++a) convert_agent(agents[a], d, order, &AL[a]);
   for (int a = 0; a < A; ++a)
     if (AL[a].rc != DCORA_OK) {
@@ -238,7 +253,7 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
                           const std::vector<int> &n, const std::vector<int> &l,
                           const std::vector<int> &poff, const dcora_halo_segment *segs,
                           int nseg, const int64_t *rowptr, const int32_t *col,
-                          const double *val, HostCoupling *out) {
+                          const double *val, const int64_t *row_key, HostCoupling *out) {
   HostCoupling &C = *out;
   const int dh = d + 1;
   const int A = (int)n.size();
@@ -309,9 +324,15 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
       }
     }
   }
+  // accumulation order of the sources of an output column: ascending key.  With the
+  // caller's keys (the GLOBAL column of every extended row) G is summed in the same order
+  // however the agents are dealt to ranks: iterates are bit-identical across world sizes.
+  std::vector<int64_t> keyI(KE);
+  for (int64_t R = 0; R < KE; ++R) keyI[r2i[R]] = row_key ? row_key[R] : r2i[R];
+  auto by_key = [&](int a, int b) { return keyI[a] < keyI[b] || (keyI[a] == keyI[b] && a < b); };
   C.browptr.assign(np + 1, 0);
   for (int i = 0; i < np; ++i) {
-    std::sort(cols[i].begin(), cols[i].end());
+    std::sort(cols[i].begin(), cols[i].end(), by_key);
     C.browptr[i + 1] = C.browptr[i] + (int)cols[i].size();
   }
   C.bcol.resize(C.browptr[np]);
@@ -341,7 +362,7 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
         const int i = oblk[ci];
         const int *b0 = C.bcol.data() + C.browptr[i];
         const int *b1 = C.bcol.data() + C.browptr[i + 1];
-        const int64_t q = std::lower_bound(b0, b1, blk[ri]) - C.bcol.data();
+        const int64_t q = std::find(b0, b1, blk[ri]) - C.bcol.data();
         // component of the output column / source column inside its block
         const int a_out = ci - C.prowcol[i], b_src = ri - blk[ri];
         C.bval[(size_t)q * dh * dh + a_out * dh + b_src] += val[p];
@@ -350,6 +371,19 @@ int build_coupling_layout(int d, int order, const std::vector<int64_t> &coff,
         C.rem_col[w] = ri;
         C.rem_val[w] = val[p];
       }
+    }
+  }
+  if (row_key) {
+    std::vector<std::pair<int, double>> tmp;
+    for (size_t s = 0; s + 1 < C.rem_rowptr.size(); ++s) {
+      const int b = C.rem_rowptr[s], e = C.rem_rowptr[s + 1];
+      tmp.clear();
+      for (int w = b; w < e; ++w) tmp.emplace_back(C.rem_col[w], C.rem_val[w]);
+      std::stable_sort(tmp.begin(), tmp.end(),
+                       [&](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+                         return by_key(x.first, y.first);
+                       });
+      for (int w = b; w < e; ++w) { C.rem_col[w] = tmp[w - b].first; C.rem_val[w] = tmp[w - b].second; }
     }
   }
   return DCORA_OK;

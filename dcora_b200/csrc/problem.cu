@@ -302,7 +302,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       tape_warps = std::max(tape_warps, trsv_warps_for((double)(H.coff[a + 1] - H.coff[a])));
     std::vector<int> rcs(num_agents, DCORA_OK);
     const int dh = d + 1;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(setup_threads())
     for (int a = 0; a < num_agents; ++a) {
       const dcora_agent_desc &g = agents[a];
       const int k = dh * g.n + g.l + g.b;

@@ -60,6 +60,13 @@ extern "C" {
 int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
                                int32_t nseg, const int32_t *rowptr,
                                const int32_t *col, const double *val) {
+  return dcora_problem_set_coupling_keyed(p, segs, nseg, rowptr, col, val, nullptr);
+}
+
+int dcora_problem_set_coupling_keyed(dcora_problem *p, const dcora_halo_segment *segs,
+                                     int32_t nseg, const int32_t *rowptr,
+                                     const int32_t *col, const double *val,
+                                     const int64_t *row_key) {
   if (!p || !rowptr || nseg < 0 || (nseg > 0 && !segs)) return DCORA_ERR_ARG;
   DCORA_CUDA(cudaSetDevice(p->M->device));
   DeviceMatrices &M = *p->M;
@@ -71,7 +78,7 @@ int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
   for (int64_t i = 0; i <= KE; ++i) rp[i] = rowptr[i];
   HostCoupling H;
   DCORA_TRY(build_coupling_layout(M.d, M.order, M.coff, M.n, M.l, M.poff, segs, nseg,
-                                  rp.data(), col, val, &H));
+                                  rp.data(), col, val, row_key, &H));
   auto C = std::make_shared<DeviceCoupling>();
   C->device = M.device;
   C->KH = H.KH;
@@ -266,6 +273,18 @@ int dcora_problem_combine_project(dcora_problem *p, double a, const double *Am,
   DCORA_TRY(launch_axpby(p, y, -1, a, x, -1, b, y, F_USER));
   DCORA_TRY(launch_project_manifold(p, y, o, F_USER));
   return export_matrix(p, o, OUT, p->r);
+}
+
+int dcora_problem_combine(dcora_problem *p, double a, const double *Am, double b,
+                          const double *Bm, double *OUT) {
+  if (!p || !Am || !Bm || !OUT) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  double *x = p->vec(WS_IO0), *y = p->vec(WS_IO1);
+  if (!x || !y) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, Am, x, p->r));
+  DCORA_TRY(import_matrix(p, Bm, y, p->r));
+  DCORA_TRY(launch_axpby(p, y, -1, a, x, -1, b, y, -1));
+  return export_matrix(p, y, OUT, p->r);
 }
 
 }  // extern "C"

@@ -52,6 +52,7 @@ class RankPlan:
     coupling: sp.csr_matrix  # (K + world*seg_cols, K)  [or (K, K) when world == 1]
     colors: np.ndarray      # colour of every GLOBAL agent
     num_colors: int
+    row_key: np.ndarray = None   # (K + world*seg_cols): global column behind every coupling row
 
     @property
     def seg_cols(self):
@@ -77,7 +78,8 @@ def make_plans(gp: GlobalProblem, world: int, cross=None):
     if world == 1:
         a0, a1 = blocks[0]
         return [RankPlan(0, 1, a0, a1, 0, gp.K, (0, 0, 0), np.zeros(0, np.int32),
-                         cross.tocsr(), colors, ncol, dh=dh)]
+                         cross.tocsr(), colors, ncol, dh=dh,
+                         row_key=np.arange(gp.K, dtype=np.int64))]
     # public columns per rank: rows of `cross` with an entry in another rank's column
     row_of = np.repeat(np.arange(gp.K), np.diff(cross.indptr))
     inter = roc[row_of] != roc[cross.indices]
@@ -96,6 +98,7 @@ def make_plans(gp: GlobalProblem, world: int, cross=None):
     seg_cols = dh * n_s + l_s + b_s
     # global column -> halo column (extended index relative to the rank's K is added later)
     halo_of = -np.ones(gp.K, np.int64)
+    halo_key = -np.ones(world * seg_cols, np.int64)      # global column behind a halo column
     packs = []
     for r in range(world):
         poses, sph, lmk = pub[r]
@@ -120,6 +123,7 @@ def make_plans(gp: GlobalProblem, world: int, cross=None):
         if len(lmk):
             seg_ref[lm_pos] = gp.lmk_col(lmk); valid[lm_pos] = True
         halo_of[seg_ref[valid]] = r * seg_cols + np.nonzero(valid)[0]
+        halo_key[r * seg_cols + np.nonzero(valid)[0]] = seg_ref[valid]
         pk = np.where(valid, seg_ref - c0, 0)
         packs.append(pk.astype(np.int32))
     plans = []
@@ -132,7 +136,9 @@ def make_plans(gp: GlobalProblem, world: int, cross=None):
         rows = np.where(local, sub.row - c0, K + halo_of[sub.row])
         assert (rows >= 0).all() and (halo_of[sub.row[~local]] >= 0).all()
         C = sp.csr_matrix((sub.data, (rows, sub.col)), shape=(K + world * seg_cols, K))
-        plans.append(RankPlan(r, world, a0, a1, c0, K, seg, packs[r], C, colors, ncol, dh=dh))
+        key = np.concatenate([np.arange(c0, c1, dtype=np.int64), halo_key])
+        plans.append(RankPlan(r, world, a0, a1, c0, K, seg, packs[r], C, colors, ncol, dh=dh,
+                              row_key=key))
     return plans
 
 
@@ -161,21 +167,28 @@ class RBCD:
     def __init__(self, gp: GlobalProblem, r: int, rank=0, world=1, device=0,
                  params: ROptParameters | None = None, precond=True, group=None,
                  plan: RankPlan | None = None, diag=None, acceleration=False,
-                 restart_interval=30):
+                 restart_interval=30, _problem=None):
         import torch
         self.torch = torch
         self.gp, self.r, self.rank, self.world, self.group = gp, r, rank, world, group
-        if plan is None or diag is None:
-            blocks = rank_agents(gp.A, world)
-            diag, cross = gp.split(agents=range(*blocks[rank]))
-            plan = make_plans(gp, world, cross)[rank]
-        self.plan = plan
-        reg = None if not precond else ("auto_ra" if gp.ra else 0.1)
-        agents = [AgentData(n=int(gp.n_a[a]), l=int(gp.l_a[a]), b=int(gp.b_a[a]), Q=diag[a],
-                            precond_reg=reg) for a in range(plan.a0, plan.a1)]
-        self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
-        segs = [plan.seg] * world if world > 1 else []
-        self.P.set_coupling(plan.coupling, segs)
+        self.precond = precond
+        if _problem is not None:
+            # another rank of the same partitioned problem (with_rank): the data matrices,
+            # the Cholesky factors and the coupling are shared on the device
+            self.plan = plan
+            self.P = _problem
+        else:
+            if plan is None or diag is None:
+                blocks = rank_agents(gp.A, world)
+                diag, cross = gp.split(agents=range(*blocks[rank]))
+                plan = make_plans(gp, world, cross)[rank]
+            self.plan = plan
+            reg = None if not precond else ("auto_ra" if gp.ra else 0.1)
+            agents = [AgentData(n=int(gp.n_a[a]), l=int(gp.l_a[a]), b=int(gp.b_a[a]), Q=diag[a],
+                                precond_reg=reg) for a in range(plan.a0, plan.a1)]
+            self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
+            segs = [plan.seg] * world if world > 1 else []
+            self.P.set_coupling(plan.coupling, segs, row_key=plan.row_key)
         # the iterate lives in ONE device buffer (self.X) that only the library writes
         self.P.set_iterate_tracking(True)
         self.params = params or ROptParameters()
@@ -199,6 +212,15 @@ class RBCD:
             # several iterate-sized buffers (X, Y, V, XPrev) are exchanged per step:
             # no single tracked buffer
             self.P.set_iterate_tracking(False)
+
+    def with_rank(self, r):
+        """The same partitioned problem at another relaxation rank (next staircase level):
+        Q, the factors and the coupling stay on the device (dcora_problem_clone_rank)."""
+        P = self.P.with_rank(r)
+        P.KH = self.P.KH
+        return RBCD(self.gp, r, self.rank, self.world, self.device.index, self.params,
+                    self.precond, self.group, plan=self.plan, acceleration=self.acc,
+                    restart_interval=self.restart_interval, _problem=P)
 
     # -- state ---------------------------------------------------------------
     def set_X(self, X_global):
@@ -311,18 +333,70 @@ class RBCD:
         V = self.P.combine_project(1.0, self.V, self.gamma, Xn - Y, None)
         self.X, self.V, self.Y = Xn, V, Y
 
-    def monitor(self):
+    def monitor(self, per_agent=False):
         """Global cost f and Riemannian gradient norm (the centralised
-        evaluation of MultiRobotExample.cpp:264-281, computed blockwise)."""
+        evaluation of MultiRobotExample.cpp:264-281, computed blockwise).  With
+        `per_agent` also the gradient norm of every agent's block (all A agents of the job):
+        the quantity the block selection rules rank (MultiRobotExample.cpp:288-305)."""
         self.exchange()
         self.P.update_G(self.X, self.H, None)
         quad, lin = self.P.cost_terms(self.X)
         gn = np.atleast_1d(self.P.RieGradNorm(self.X))
         f = float(np.sum(quad) + 0.5 * np.sum(lin))
         g2 = float(np.sum(gn ** 2))
+        norms = np.asarray(gn, dtype=np.float64)
         if self.world > 1:
             import torch.distributed as dist
             v = self.torch.tensor([f, g2], dtype=self.torch.float64, device=self.device)
             dist.all_reduce(v, group=self.group)
             f, g2 = float(v[0]), float(v[1])
+            if per_agent:
+                full = self.torch.zeros(self.gp.A, dtype=self.torch.float64, device=self.device)
+                full[self.plan.a0:self.plan.a1] = self.torch.from_numpy(norms).to(self.device)
+                dist.all_reduce(full, group=self.group)
+                norms = full.cpu().numpy()
+        if per_agent:
+            return f, float(np.sqrt(g2)), norms
         return f, float(np.sqrt(g2))
+
+    # -- the reference drivers' one-agent-per-iteration loop ------------------------
+    def run_selected(self, num_iters, selection="greedy", gradnorm_tol=0.0, seed=0,
+                     integer_norms=False, first=0, log=None):
+        """examples/MultiRobotExample.cpp:223-307 / MultiRobotExample_RASLAM.cpp:290-452:
+        ONE selected agent takes iterate(true) per iteration, every other agent
+        iterate(false); after the centralised evaluation the next agent is chosen by the
+        BlockSelectionRule (include/DCORA/DCORA_types.h:54):
+
+          "greedy"   the agent whose block of the Riemannian gradient is largest
+                     (first of equals, std::max_element);
+          "uniform"  an agent drawn uniformly (std::uniform_int_distribution).
+
+        An agent without neighbours keeps the turn.  `integer_norms` reproduces the RASLAM
+        example's std::map<unsigned, unsigned> (block norms truncated to integers before the
+        comparison, MultiRobotExample_RASLAM.cpp:404).  Returns the list of
+        (selected agent, f, gradnorm) per iteration."""
+        assert selection in ("greedy", "uniform")
+        rng = np.random.default_rng(seed)
+        A = self.gp.A
+        nbrs = np.array([len(a) for a in self.gp.agent_graph()])
+        selected = int(first)
+        hist = []
+        for it in range(int(num_iters)):
+            active = np.zeros(self.A_local, np.uint8)
+            if self.plan.a0 <= selected < self.plan.a1:
+                active[selected - self.plan.a0] = 1
+            self.step(active)
+            f, gn, norms = self.monitor(per_agent=True)
+            hist.append((selected, f, gn))
+            if log:
+                log(f"iter {it} robot {selected} cost {2 * f:.6f} gradnorm {gn:.6g}")
+            if gn < gradnorm_tol:
+                break
+            if nbrs[selected] == 0:
+                continue
+            if selection == "greedy":
+                key = np.floor(norms) if integer_norms else norms
+                selected = int(np.argmax(key))
+            else:
+                selected = int(rng.integers(0, A))
+        return hist

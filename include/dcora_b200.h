@@ -231,6 +231,15 @@ typedef struct {
 int dcora_problem_set_coupling(dcora_problem *p, const dcora_halo_segment *segs,
                                int32_t nseg, const int32_t *rowptr,
                                const int32_t *col, const double *val);
+/* The same with an accumulation order: row_key[K + KH] gives every row of C (every source
+ * column of [X | H]) a key, and the contributions to one column of G are summed in ascending
+ * key order (NULL: ascending row).  With the GLOBAL column number of each source as key the
+ * sum does not depend on how the agents are dealt to processes: the iterates of an N-rank
+ * run are bit-identical to the 1-rank run's. */
+int dcora_problem_set_coupling_keyed(dcora_problem *p, const dcora_halo_segment *segs,
+                                     int32_t nseg, const int32_t *rowptr,
+                                     const int32_t *col, const double *val,
+                                     const int64_t *row_key);
 int64_t dcora_problem_halo_dim(const dcora_problem *p); /* KH */
 
 /* Graph::setNeighborStates + constructG (src/Graph.cpp:333-340,565-577) for
@@ -266,6 +275,27 @@ int dcora_problem_set_iterate_tracking(dcora_problem *p, int32_t on);
 int dcora_problem_load_iterate(dcora_problem *p, const double *X_host, double *X_device);
 int dcora_problem_store_iterate(dcora_problem *p, const double *X_device, double *X_host);
 
+/* Rounding (src/DCORA_utils.cpp).
+ *
+ * dcora_project_to_rotation_group: projectToRotationGroup (:1661-1675), host, d x d
+ * column-major in and out (d = 2 or 3).
+ *
+ * dcora_problem_round_solution: projectSolutionRASLAM (:1984-2031) for
+ * the whole batch treated as one solution: X is r x K (reference ordering, host or device),
+ * Xd is d x K in the same ordering.  Rank-d truncation of X through the r x r Gram matrix,
+ * reflection vote over the rotation blocks, rotations to SO(d), unit spheres normalised.
+ * The truncation is unique up to the sign of each of its d rows; the vote removes the
+ * improper part, so two implementations agree up to diag(+-1) of determinant +1.
+ *
+ * dcora_problem_align_trajectory: alignLiftedTrajectoryToFrame (:2262-2289).  Tw0 is the
+ * r x (d+1) lifted frame [R0 t0] column-major; Td (d x K) = R0^T X with every rotation block
+ * projected to SO(d) and R0^T ta subtracted from every translation (and landmark), ta = t0
+ * (is_global) or the first translation of R0^T X (local; needs r == d as in the reference). */
+int dcora_project_to_rotation_group(const double *M, int32_t d, double *R);
+int dcora_problem_round_solution(dcora_problem *p, const double *X, double *Xd);
+int dcora_problem_align_trajectory(dcora_problem *p, const double *X, const double *Tw0,
+                                   int32_t is_global, double *Td);
+
 /* Per-agent 0.5 <X Q, X> and <X, G>: the global cost of the partitioned
  * problem is sum_a quad_a + 0.5 lin_a (cross terms appear in two agents). */
 int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,
@@ -277,6 +307,9 @@ int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out
 int dcora_problem_combine_project(dcora_problem *p, double a, const double *A,
                                   double b, const double *B, const uint8_t *active,
                                   double *OUT);
+/* OUT = a * A + b * B (no projection; the X - Y term of Agent::updateV). */
+int dcora_problem_combine(dcora_problem *p, double a, const double *A, double b,
+                          const double *B, double *OUT);
 
 /* K1 in isolation, for roofline measurement: runs the Q-SpMM `iters` times on
  * device-resident data and returns the mean kernel time (CUDA events on the
@@ -315,6 +348,12 @@ int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, const uint8_t *activ
 int dcora_selfcheck_layout(const dcora_agent_desc *agents, int32_t num_agents,
                            int32_t r, int32_t d, int32_t order,
                            double *max_abs_err);
+int dcora_selfcheck_coupling(const dcora_agent_desc *agents, int32_t num_agents,
+                             int32_t r, int32_t d, int32_t order,
+                             const dcora_halo_segment *segs, int32_t nseg,
+                             const int32_t *rowptr, const int32_t *col, const double *val,
+                             const int64_t *row_key, double *max_abs_err,
+                             int64_t *order_violations);
 int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const int32_t *col,
                              const double *val, int32_t dh, int32_t npose,
                              double reg, double *rel_residual,

@@ -140,3 +140,19 @@ def project_solution_ra(L: mf.Layout, X):
         y = Xp[:, Ld.sph]
         Xp[:, Ld.sph] = y / np.linalg.norm(y, axis=0)
     return Xp
+
+
+def align_lifted_trajectory(X, Tw0, d, is_global=True):
+    """alignLiftedTrajectoryToFrame (DCORA_utils.cpp:2262-2289).  X: (r, (d+1) n) pose-graph
+    ordering, Tw0: (r, d+1) lifted frame.  Returns the (d, (d+1) n) trajectory."""
+    r, k = X.shape
+    n = k // (d + 1)
+    R0T = Tw0[:, :d].T
+    T = R0T @ X
+    ta = Tw0[:, d] if is_global else T[:, d]
+    t0 = R0T @ ta          # (local alignment needs r == d, as in the reference)
+    for i in range(n):
+        c = i * (d + 1)
+        T[:, c:c + d] = mf.project_rotation(T[:, c:c + d])
+        T[:, c + d] -= t0
+    return T

@@ -122,17 +122,41 @@ class RBCD:
         for c in range(int(np.max(colors)) + 1):
             self.iterate(np.nonzero(np.asarray(colors) == c)[0])
 
-    def monitor(self):
+    def monitor(self, per_agent=False):
         """Global cost and Riemannian gradient norm, block by block
         (MultiRobotExample.cpp:264-281 evaluates the centralised problem)."""
         G = (self.Ct @ self.X.T).T
         f = 0.0
-        g2 = 0.0
+        norms = []
         for b in self.blocks:
             s = slice(b.c0, b.c1)
             Xa = self.X[:, s]
             XQ = b.P.XQ(Xa)
             f += 0.5 * np.sum(XQ * Xa) + 0.5 * np.sum(Xa * G[:, s])
             rg = mf.tangent_project(b.L, Xa, XQ + G[:, s])
-            g2 += np.sum(rg * rg)
-        return f, np.sqrt(g2)
+            norms.append(np.sqrt(np.sum(rg * rg)))
+        norms = np.array(norms)
+        gn = np.sqrt(np.sum(norms ** 2))
+        return (f, gn, norms) if per_agent else (f, gn)
+
+    def run_selected(self, num_iters, selection="greedy", gradnorm_tol=0.0, seed=0,
+                     integer_norms=False, first=0):
+        """The driver loop itself (MultiRobotExample.cpp:223-307, block selection :288-305;
+        MultiRobotExample_RASLAM.cpp:404-452 for the rule switch and its integer-valued
+        std::map): one selected agent per iteration, next one greedy / uniform."""
+        rng = np.random.default_rng(seed)
+        has_nbr = np.array([self.Ct[b.c0:b.c1].nnz > 0 for b in self.blocks])
+        selected, hist = int(first), []
+        for _ in range(num_iters):
+            self.iterate([selected])
+            f, gn, norms = self.monitor(per_agent=True)
+            hist.append((selected, f, gn))
+            if gn < gradnorm_tol:
+                break
+            if not has_nbr[selected]:
+                continue
+            if selection == "greedy":
+                selected = int(np.argmax(np.floor(norms) if integer_norms else norms))
+            else:
+                selected = int(rng.integers(0, self.A))
+        return hist

@@ -141,3 +141,41 @@ def write_g2o(path, meas, name=None):
                 vals = [pp.t[e][0], pp.t[e][1], th[e], tau, 0.0, 0.0, tau, 0.0, kap]
                 fh.write(f"EDGE_SE2 {pp.p1[e]} {pp.p2[e]} " +
                          " ".join(f"{v:.17g}" for v in vals) + "\n")
+
+
+def oracle_measurements(M, part):
+    """The reverse of product_measurements: the product's global-index Measurements +
+    Partition -> the oracle's per-robot (robot id, local index) measurement arrays.  Unit
+    spheres are numbered per source robot in measurement order (DCORA_utils.cpp:1092-1094)."""
+    rob_p = np.asarray(part.robot_of_pose, np.int64)
+    rob_l = np.asarray(part.robot_of_lmk, np.int64)
+    A = int(part.num_robots)
+
+    def local(rob):
+        loc = np.zeros(len(rob), np.int64)
+        for a in range(A):
+            sel = rob == a
+            loc[sel] = np.arange(int(sel.sum()))
+        return loc
+    loc_p, loc_l = local(rob_p), local(rob_l)
+    d, n = M.d, M.n
+    pp = dataio.PosePose(d, rob_p[M.pp_i], loc_p[M.pp_i], rob_p[M.pp_j], loc_p[M.pp_j],
+                         M.pp_R, M.pp_t, M.pp_kappa, M.pp_tau, M.pp_w)
+    pl = dataio.PoseLandmark(d, rob_p[M.pl_i], loc_p[M.pl_i], rob_l[M.pl_j], loc_l[M.pl_j],
+                             M.pl_t, M.pl_tau, M.pl_w)
+
+    def endpoint(v):
+        is_l = v >= n
+        vp, vl = np.where(is_l, 0, v), np.where(is_l, v - n, 0)
+        rob = np.where(is_l, rob_l[vl] if len(rob_l) else 0, rob_p[vp])
+        idx = np.where(is_l, loc_l[vl] if len(loc_l) else 0, loc_p[vp])
+        return rob, idx, np.where(is_l, dataio.LANDMARK, dataio.POSE)
+    r1, p1, t1 = endpoint(M.rg_i)
+    r2, p2, t2 = endpoint(M.rg_j)
+    sph = np.zeros(len(r1), np.int64)
+    cnt = np.zeros(A, np.int64)
+    for e in range(len(r1)):
+        sph[e] = cnt[r1[e]]
+        cnt[r1[e]] += 1
+    rg = dataio.Range(r1, p1, r2, p2, t1, t2, sph, M.rg_range, M.rg_prec, M.rg_w)
+    return dataio.Measurements(d, pp, pl, rg)

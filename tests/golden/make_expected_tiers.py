@@ -1,0 +1,84 @@
+"""Oracle known-answer for configs[1]: the Riemannian staircase on tiers.pyfg.
+
+    python tests/golden/make_expected_tiers.py          (build container, minutes of CPU)
+
+Follows examples/SingleRobotExample_RASLAM.cpp:182-283: from r = d, optimize (RTR, the
+example's 200 x 200 iterations, gradnorm_tol 1e-4) -> dual certificate S = Q - Lambda ->
+fastVerification(eta = 1e-4) -> escapeSaddle to rank r + 1, until S + eta I is PSD.  The
+start is the data file's ground truth lifted with [I; 0] (the example's non-odometry branch:
+deterministic, unlike its random landmarks).  The optimisation runs on oracle/native (C++ -O3
+restatement of the same RTR/tCG, cross-checked against oracle/solver.py in
+tests/test_oracle_native.py); certificate, eigenvalue and escape on the scipy oracle.
+Writes the per-level record and the final answer to tests/golden/expected.json["tiers_staircase"].
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import certify, graph, manifold as mf, native, solver  # noqa: E402
+from tests.common import load_golden  # noqa: E402
+
+ETA = 1e-4          # min_eig_num_tol of the example
+TOL = 1e-4          # gradnorm_tol, gradient_tolerance, preconditioned_gradient_tolerance
+R_MAX = 8
+
+
+def main():
+    meas, info = load_golden("tiers")
+    d = info["d"]
+    t_all = time.time()
+    levels = []
+    X = None
+    for r in range(d, R_MAX):
+        g = graph.Graph(0, r, d, ra=True).set_measurements(meas)
+        Q = g.quadratic_matrix()
+        L = mf.Layout(r, d, g.n, g.l, g.b, ra=True)
+        reg = graph.precond_regularization(Q, True)
+        if X is None:
+            X = np.zeros((r, L.k))
+            X[:d] = info["X_gt"]
+            X = mf.project_manifold(L, X)
+        t0 = time.time()
+        prob = native.AgentProblem(L, Q, reg)
+        Xopt, st = prob.update(np.zeros((r, L.k), order="F"), np.asfortranarray(X),
+                               max_outer=200, max_inner=200, tol=TOL, delta0=100.0)
+        P = solver.QuadraticProblem(L, Q, precond_reg=reg)
+        f, gn = P.f(Xopt), P.rgrad_norm(Xopt)
+        S = certify.certificate_matrix(L, Xopt, Q)
+        psd, theta, v = certify.fast_verification(S, ETA)
+        lam = certify.lambda_min(S)
+        lev = dict(r=r, fOpt=f, gradNormOpt=gn, outer=int(st["outer"]), inner=int(st["inner"]),
+                   is_psd=bool(psd), lambda_min=lam, theta=None if theta is None else float(theta),
+                   seconds=time.time() - t0)
+        print(lev, flush=True)
+        levels.append(lev)
+        if psd:
+            break
+        Ln = L.with_rank(r + 1)
+        gn1 = graph.Graph(0, r + 1, d, ra=True).set_measurements(meas)
+        Pn = solver.QuadraticProblem(Ln, gn1.quadratic_matrix(), precond_reg=reg)
+        X, ok = solver.escape_saddle(Pn, Xopt, theta, v, TOL, TOL, is_second_order=True)
+        if not ok:
+            print("escape failed", flush=True)
+            break
+    path = os.path.join(HERE, "expected.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    fin = levels[-1]
+    out["tiers_staircase"] = dict(init="gt", eta=ETA, gradnorm_tol=TOL, RTR_iterations=200,
+                                  RTR_tCG_iterations=200, r_min=d, levels=levels,
+                                  certified=fin["is_psd"], rank=fin["r"], fOpt=fin["fOpt"],
+                                  cost_2f=2 * fin["fOpt"], lambda_min=fin["lambda_min"],
+                                  oracle_seconds=time.time() - t_all)
+    with open(path, "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

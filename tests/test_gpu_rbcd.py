@@ -233,3 +233,28 @@ def test_distributed_certificate_matches_the_centralised_one():
     res = certify_distributed(G, 1e-3, tol=1e-10)
     assert res.is_psd and bool(cen.is_psd)
     assert abs(res.lambda_min - cen.lambda_min) <= 1e-6 * max(abs(cen.lambda_min), 1e-3)
+
+
+@pytest.mark.parametrize("name,robots,selection,acc", [
+    ("smallGrid3D", 5, "greedy", False), ("smallGrid3D", 5, "uniform", False),
+    ("range_aided_slam_test_3d", 2, "greedy", True), ("kitti_00", 8, "greedy", False)])
+def test_block_selection_rules_follow_the_oracle(name, robots, selection, acc):
+    # the reference drivers' loop (MultiRobotExample.cpp:223-307): one selected agent per
+    # iteration, the next one by BlockSelectionRule Greedy / Uniform
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    r = 5
+    gp, blocks, cross = _setup(name, robots, r)
+    X0 = _random_X(blocks, r, gp.K, 3)
+    G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0), acceleration=acc)
+    G.set_X(X0)
+    O = orbcd.RBCD(blocks, cross, solver.ROptParameters(), acceleration=acc)
+    O.set_X(X0)
+    iters = 12
+    hg = G.run_selected(iters, selection, seed=4)
+    ho = O.run_selected(iters, selection, seed=4)
+    assert [h[0] for h in hg] == [h[0] for h in ho]          # same agents, same order
+    assert len(set(h[0] for h in hg)) > 1
+    for (_, fg, gg), (_, fo, go_) in zip(hg, ho):
+        assert abs(fg - fo) <= 1e-6 * abs(fo)
+        assert abs(gg - go_) <= 1e-4 * go_

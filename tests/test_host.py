@@ -151,3 +151,69 @@ def test_block_trsv_schedule(lib, name, ordering):
     if ordering == 1 and Q.shape[0] > 2000:
         # the block elimination tree of the ND ordering is shallow
         assert lf.value <= 64, (lf.value, nb.value)
+
+
+def test_project_to_rotation_group_matches_oracle():
+    """dcora_project_to_rotation_group (host entry of the rounding code) against the
+    oracle's SVD projection, including reflections and near-singular inputs."""
+    import dcora_b200 as dc
+    from dcora_b200.api import project_to_rotation_group
+    from oracle import manifold as mf
+    rng = np.random.default_rng(0)
+    for d in (2, 3):
+        for trial in range(40):
+            M = rng.standard_normal((d, d))
+            if trial % 4 == 1:
+                M[:, -1] = -M[:, -1]
+            if trial % 4 == 2:      # close to a rotation
+                M = mf.project_rotation(M) + 1e-3 * rng.standard_normal((d, d))
+            if trial % 4 == 3:      # rank deficient + tiny noise
+                M[:, 0] = M[:, 1] * 2 + 1e-9 * rng.standard_normal(d)
+            R = project_to_rotation_group(M)
+            want = mf.project_rotation(M)
+            assert np.allclose(R @ R.T, np.eye(d), atol=1e-12)
+            assert abs(np.linalg.det(R) - 1.0) < 1e-12
+            if trial % 4 != 3:
+                assert np.allclose(R, want, atol=1e-9), (d, trial)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("S,robots", [(5, 6), (6, 8)])
+def test_coupling_layout_is_exact_and_key_ordered(lib, S, robots, world):
+    """build_coupling_layout with the global-column keys of rbcd.make_plans: the converted
+    block / remainder structures reproduce [X | H] * C, and every output column's sources are
+    stored in ascending key order (the rank-count-independent accumulation order)."""
+    from dcora_b200 import graph as pg, rbcd, synthetic
+    from dcora_b200._lib import HaloSegment
+    meas, gt, idx = synthetic.grid3d(S, 0.2, seed=S)
+    gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, robots))
+    for plan in rbcd.make_plans(gp, world):
+        diag, _ = gp.split(agents=range(plan.a0, plan.a1))
+        keep = []
+        descs = (AgentDesc * (plan.a1 - plan.a0))()
+        for i, a in enumerate(range(plan.a0, plan.a1)):
+            rp, ci, v = diag[a]
+            rp, ci, v = rp.astype(np.int32), ci.astype(np.int32), v.astype(np.float64)
+            keep += [rp, ci, v]
+            descs[i].n, descs[i].l, descs[i].b = int(gp.n_a[a]), int(gp.l_a[a]), int(gp.b_a[a])
+            descs[i].rowptr = rp.ctypes.data_as(_lib.c_int32_p)
+            descs[i].col = ci.ctypes.data_as(_lib.c_int32_p)
+            descs[i].val = v.ctypes.data_as(_lib.c_double_p)
+            descs[i].precond_reg = 0.1
+        nseg = world if world > 1 else 0
+        segs = (HaloSegment * max(1, nseg))()
+        for s in range(nseg):
+            segs[s].n, segs[s].l, segs[s].b = plan.seg
+        Cm = plan.coupling.tocsr()
+        rp, ci, v = Cm.indptr.astype(np.int32), Cm.indices.astype(np.int32), Cm.data.astype(np.float64)
+        key = np.ascontiguousarray(plan.row_key, dtype=np.int64)
+        err, bad = C.c_double(-1), C.c_int64(-1)
+        rc = lib.dcora_selfcheck_coupling(descs, plan.a1 - plan.a0, 4, 3, 1, segs, nseg,
+                                          rp.ctypes.data_as(_lib.c_int32_p),
+                                          ci.ctypes.data_as(_lib.c_int32_p),
+                                          v.ctypes.data_as(_lib.c_double_p),
+                                          key.ctypes.data_as(C.POINTER(C.c_int64)),
+                                          C.byref(err), C.byref(bad))
+        assert rc == 0, lib.dcora_last_error()
+        assert err.value <= 1e-9 * max(1.0, np.abs(v).max() if len(v) else 1.0)
+        assert bad.value == 0

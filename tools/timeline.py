@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--range-fraction", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--restart", action="store_true",
+                    help="profile the first iterations from the initial guess (what bench.py times)")
     a = ap.parse_args()
     import torch
     from torch.profiler import profile, ProfilerActivity
@@ -32,9 +34,12 @@ def main():
     log = lambda m: print("[timeline] " + m, file=sys.stderr, flush=True)
     meas, gt, idx, gp = bench.build_problem(a, log)
     S = rbcd.RBCD(gp, a.rank, params=dc.ROptParameters(time_bound_s=0.0))
-    S.set_X(bench.initial_X(a, meas, idx, gp))
+    X0 = bench.initial_X(a, meas, idx, gp)
+    S.set_X(X0)
     for _ in range(3):
         S.iterate(); S.monitor()
+    if a.restart:
+        S.set_X(X0)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(a.steps):

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Time to a certified solution of a partitioned range-aided grid: RBCD(++) sweeps ->
+distributed certificate -> escape -> next rank (dcora_b200.staircase.rbcd_staircase).
+    python tools/ttc_multi.py --grid 47 --agents 16 [--no-acc]
+Under torchrun the agents are dealt to the ranks (one GPU each)."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol=0.1, eta=1e-3,
+        max_iters=1000, check_every=5, log=print, dist_rank=0, world=1, group=None, device=0,
+        r_max=None):
+    import dcora_b200 as dc
+    from dcora_b200 import graph as pg, rbcd, synthetic
+    from dcora_b200.staircase import rbcd_staircase
+    t0 = time.perf_counter()
+    meas, gt, idx = synthetic.grid3d(grid, range_fraction, seed=seed)
+    gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, agents))
+    X0 = synthetic.lifted_initial_guess(meas, idx, gp, grid, rank)
+    t1 = time.perf_counter()
+    S = rbcd.RBCD(gp, rank, rank=dist_rank, world=world, device=device, group=group,
+                  params=dc.ROptParameters(time_bound_s=0.0), acceleration=acc)
+    t2 = time.perf_counter()
+    res = rbcd_staircase(S, X0, r_max=r_max or rank + 3, eta=eta, gradnorm_tol=gradnorm_tol,
+                         max_iters=max_iters, check_every=check_every, log=log)
+    t3 = time.perf_counter()
+    return {"workload": f"synthetic {grid}^3-pose 3D grid, {int(range_fraction * 100)}% range edges, "
+                        f"{agents} agents on {world} GPU(s), RBCD{'++' if acc else ''}, r0={rank}, "
+                        f"gradnorm_tol={gradnorm_tol}, eta={eta}",
+            "poses": int(meas.n), "K": int(gp.K), "agents": agents, "certified": res.certified,
+            "rank": res.rank, "cost_2f": 2 * res.cost, "gradnorm": res.gradnorm,
+            "lambda_min": res.lambda_min, "assemble_s": t1 - t0, "factor_upload_s": t2 - t1,
+            "solve_certify_s": t3 - t2, "seconds": t3 - t0, "levels": res.levels}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=47)
+    ap.add_argument("--agents", type=int, default=16)
+    ap.add_argument("--rank", type=int, default=5)
+    ap.add_argument("--tol", type=float, default=0.1)
+    ap.add_argument("--max-iters", type=int, default=1000)
+    ap.add_argument("--check-every", type=int, default=5)
+    ap.add_argument("--no-acc", action="store_true")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch, torch.distributed as dist
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    log = (lambda m: print("[ttc] " + m, file=sys.stderr, flush=True)) if rk == 0 else None
+    out = run(a.grid, a.agents, a.rank, acc=not a.no_acc, gradnorm_tol=a.tol, max_iters=a.max_iters,
+              check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev)
+    if rk == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
