@@ -179,3 +179,54 @@ def oracle_measurements(M, part):
         cnt[r1[e]] += 1
     rg = dataio.Range(r1, p1, r2, p2, t1, t2, sph, M.rg_range, M.rg_prec, M.rg_w)
     return dataio.Measurements(d, pp, pl, rg)
+
+
+def write_pyfg(path, M, part, gt=None):
+    """Write the product's global-index Measurements + Partition as a PyFG file (the format of
+    data/*.pyfg, read by src/DCORA_utils.cpp:437-1167): robot letters A, B, ..; pose i of robot
+    R is "R<local index>", landmark j "LR<local index>".  Covariances are chosen so that the
+    reader's formulas give back kappa / tau / precision: cov_t = I / tau, cov_R = I / (2 kappa)
+    (3-D) or 1 / kappa (2-D), range cov = 1 / precision.  gt = (R (n, d, d), p (n, d)) fills
+    the VERTEX lines (identity / zero otherwise); landmarks are written at the origin."""
+    from scipy.spatial.transform import Rotation
+    d, n = M.d, M.n
+    rob_p = np.asarray(part.robot_of_pose, np.int64)
+    rob_l = np.asarray(part.robot_of_lmk, np.int64) if M.b else np.zeros(0, np.int64)
+
+    def local(rob):
+        loc = np.zeros(len(rob), np.int64)
+        for a in range(int(part.num_robots)):
+            sel = rob == a
+            loc[sel] = np.arange(int(sel.sum()))
+        return loc
+    loc_p, loc_l = local(rob_p), local(rob_l)
+    psym = [chr(65 + int(rob_p[i])) + str(int(loc_p[i])) for i in range(n)]
+    lsym = ["L" + chr(65 + int(rob_l[j])) + str(int(loc_l[j])) for j in range(M.b)]
+    Rg = gt[0] if gt is not None else np.tile(np.eye(d), (n, 1, 1))
+    pg = gt[1] if gt is not None else np.zeros((n, d))
+
+    def pose_fields(R, t):
+        if d == 2:
+            return list(t) + [float(np.arctan2(R[1, 0], R[0, 0]))]
+        return list(t) + list(Rotation.from_matrix(R).as_quat())
+
+    def upper(diag):
+        k = len(diag)
+        return [diag[i] if i == j else 0.0 for i in range(k) for j in range(i, k)]
+    f = lambda vals: " ".join(f"{v:.17g}" for v in vals)
+    with open(path, "w") as fh:
+        for i in range(n):
+            fh.write(f"VERTEX_SE{d}{':QUAT' if d == 3 else ''} 0.0 {psym[i]} {f(pose_fields(Rg[i], pg[i]))}\n")
+        for j in range(M.b):
+            fh.write(f"VERTEX_XY{'Z' if d == 3 else ''} {lsym[j]} {f(np.zeros(d))}\n")
+        for e in range(len(M.pp_i)):
+            cov = [1.0 / M.pp_tau[e]] * d + ([1.0 / (2.0 * M.pp_kappa[e])] * 3 if d == 3
+                                             else [1.0 / M.pp_kappa[e]])
+            fh.write(f"EDGE_SE{d}{':QUAT' if d == 3 else ''} 0.0 {psym[M.pp_i[e]]} {psym[M.pp_j[e]]} "
+                     f"{f(pose_fields(M.pp_R[e], M.pp_t[e]))} {f(upper(cov))}\n")
+        for e in range(len(M.pl_i)):
+            fh.write(f"EDGE_SE{d}_XY{'Z' if d == 3 else ''} 0.0 {psym[M.pl_i[e]]} {lsym[M.pl_j[e]]} "
+                     f"{f(M.pl_t[e])} {f(upper([1.0 / M.pl_tau[e]] * d))}\n")
+        for e in range(len(M.rg_i)):
+            s = [psym[v] if v < n else lsym[v - n] for v in (int(M.rg_i[e]), int(M.rg_j[e]))]
+            fh.write(f"EDGE_RANGE 0.0 {s[0]} {s[1]} {M.rg_range[e]:.17g} {1.0 / M.rg_prec[e]:.17g}\n")

@@ -258,3 +258,34 @@ def test_block_selection_rules_follow_the_oracle(name, robots, selection, acc):
     for (_, fg, gg), (_, fo, go_) in zip(hg, ho):
         assert abs(fg - fo) <= 1e-6 * abs(fo)
         assert abs(gg - go_) <= 1e-4 * go_
+
+
+def test_multi_agent_staircase_escapes_and_certifies():
+    # MultiRobotExample.cpp:172-364 as a library call: RBCD to a critical point at rank 3 (a
+    # saddle from this start, see tests/test_gpu_solver.py), distributed certificate,
+    # distributed escapeSaddle, next rank ... until S + eta I is PSD; then rounding.
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    from dcora_b200.staircase import rbcd_staircase
+    from tests.common import central_problem
+    gp, blocks, cross = _setup("smallGrid3D", 5, 3)
+    G = rbcd.RBCD(gp, 3, params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=1e-9,
+                                                  RTR_iterations=10, RTR_tCG_iterations=100))
+    X0 = mf.random_point(central_problem("smallGrid3D", 3)[0].L, np.random.default_rng(7))
+    res = rbcd_staircase(G, X0, r_max=7, eta=1e-3, gradnorm_tol=1e-4, max_iters=800,
+                         check_every=10, certify_tol=1e-9, round_solution=True)
+    assert res.certified and res.gradnorm < 1e-4
+    assert abs(2 * res.cost - 1025.3980521) < 1e-4            # the SE-Sync optimum
+    assert res.lambda_min > -1e-3
+    if len(res.levels) > 1:
+        assert not res.levels[0]["is_psd"] and res.levels[0]["theta"] < -1e-3 / 2
+        assert res.levels[-1]["r"] == res.levels[0]["r"] + len(res.levels) - 1
+        assert res.levels[1]["f"] < res.levels[0]["f"]
+    # the rounded solution is feasible at rank d and nearly as good (small noise)
+    Pd = central_problem("smallGrid3D", 3, use_precond=False)[0]
+    Xd = res.rounded
+    assert Xd.shape == (3, gp.K)
+    B = np.transpose(Xd[:, Pd.L.rot], (1, 0, 2))
+    assert np.allclose(np.einsum("nij,nkj->nik", B, B), np.eye(3), atol=1e-10)
+    assert np.allclose(np.linalg.det(B), 1.0, atol=1e-10)
+    assert res.cost <= Pd.f(Xd) <= 1.05 * res.cost
