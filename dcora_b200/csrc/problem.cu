@@ -1,6 +1,9 @@
 // Handle life-cycle, host<->device staging, and the QuadraticProblem-level
 // entry points of the C-ABI (include/dcora_b200.h).
 #include <omp.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include <cstring>
 #include <mutex>
@@ -209,8 +212,19 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
     return DCORA_ERR_CUDA;
   }
   DCORA_CUDA(cudaSetDevice(device));
+  // DCORA_SETUP_TIMING=1: where the set-up time goes (stderr)
+  const bool timing = std::getenv("DCORA_SETUP_TIMING") != nullptr;
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[dcora setup] %-28s %8.3f s\n", what,
+                 std::chrono::duration<double>(now - tprev).count());
+    tprev = now;
+  };
   HostLayout H;
   DCORA_TRY(build_layout(agents, num_agents, r, d, order, &H));
+  lap("layout (CSR -> BSR)");
   auto M = std::make_shared<DeviceMatrices>();
   M->device = device;
   M->d = d; M->order = order; M->A = H.A; M->np = H.np; M->K = H.K;
@@ -287,6 +301,7 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
     }
   }
 
+  lap("upload of Q");
   // ---- preconditioner factors (host) -> device
   bool any = false;
   for (int a = 0; a < num_agents; ++a)
@@ -355,7 +370,9 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
         set_error("Cholesky factorisation of Q + reg*I failed for agent " + std::to_string(a));
         return DCORA_ERR_FACTOR;
       }
+    lap("factorisation + tapes");
     DCORA_TRY(upload_factor(M.get(), HF, AT, tape_warps, H));
+    lap("upload of the tapes");
   }
 
   dcora_problem *p = new dcora_problem();

@@ -139,3 +139,45 @@ def test_balanced_colouring_is_valid_and_even():
     assert len(sizes) == raw.max() + 1                   # no colour added
     assert sizes.max() <= np.bincount(raw).max()         # never worse than greedy
     assert sizes.max() - sizes.min() <= max(2, np.bincount(raw).max() - np.bincount(raw).min())
+
+
+@pytest.mark.parametrize("name", ["tinyGrid3D", "smallGrid3D", "pose_graph_optimization_test_2d",
+                                  "pose_graph_optimization_test_3d"])
+def test_initialisation_matches_oracle(name):
+    # chordalInitialization / odometryInitialization (src/DCORA_solver.cpp:218-302): sparse
+    # normal equations (product) vs dense edge-by-edge least squares (oracle)
+    from dcora_b200 import init
+    from oracle import init as oinit
+    from tests.common import load_golden, product_measurements
+    meas, info = load_golden(name)
+    M, part = product_measurements(meas, 1)
+    R, t = init.chordal_initialization(M)
+    Ro, to = oinit.chordal_initialization(meas.pp, info["n"])
+    assert np.abs(R - Ro).max() < 1e-9 and np.abs(t - to).max() < 1e-8 * max(1.0, np.abs(to).max())
+    assert np.allclose(np.linalg.det(R), 1.0) and np.allclose(R[0], np.eye(M.d))
+    if np.all(np.isin(np.arange(info["n"] - 1), M.pp_i[M.pp_j == M.pp_i + 1])):
+        R2, t2 = init.odometry_initialization(M)
+        Ro2, to2 = oinit.odometry_initialization(meas.pp, info["n"])
+        assert np.abs(R2 - Ro2).max() < 1e-12 and np.abs(t2 - to2).max() < 1e-10 * max(1.0, np.abs(to2).max())
+    if name.startswith("pose_graph_optimization_test"):
+        # noiseless fixture: the chordal solution IS the ground truth in the frame of pose 0
+        gp = pg.GlobalProblem(M, part)
+        X = init.lift(gp, R, t, M.d + 1)
+        assert 0.5 * np.sum((X @ gp.Q()) * X) < 1e-9
+
+
+def test_chordal_initialisation_beats_the_spanning_tree_guess():
+    from dcora_b200 import init
+    meas, gt, idx = synthetic.grid3d(6, 0.1, seed=1)
+    gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, 4))
+    Q = gp.Q()
+    cost = lambda X: 0.5 * float(np.sum((X @ Q) * X))
+    Xc = init.lift(gp, *init.chordal_initialization(meas), 5)
+    Xs = synthetic.lifted_initial_guess(meas, idx, gp, 6, 5)
+    Xo = init.lift(gp, *init.odometry_initialization(meas), 5)
+    assert cost(Xc) < 0.2 * cost(Xs) < cost(Xo)
+    # feasible: rotations orthonormal, unit spheres of norm one
+    i = np.arange(meas.n)
+    B = Xc[:, gp.rot_cols(i)].transpose(1, 0, 2)
+    assert np.allclose(np.einsum("nri,nrj->nij", B, B), np.eye(3), atol=1e-12)
+    assert np.allclose(np.linalg.norm(Xc[:, gp.sphere_col(np.arange(len(meas.rg_i)))], axis=0), 1.0)

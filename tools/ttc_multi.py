@@ -44,6 +44,8 @@ if __name__ == "__main__":
     ap.add_argument("--max-iters", type=int, default=1000)
     ap.add_argument("--check-every", type=int, default=5)
     ap.add_argument("--no-acc", action="store_true")
+    ap.add_argument("--range-fraction", type=float, default=0.1,
+                    help="0: pose graph only (the synthetic stand-in of the absent g2o100k, configs[3])")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rk = int(os.environ.get("RANK", "0"))
@@ -53,7 +55,7 @@ if __name__ == "__main__":
         torch.cuda.set_device(dev)
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     log = (lambda m: print("[ttc] " + m, file=sys.stderr, flush=True)) if rk == 0 else None
-    out = run(a.grid, a.agents, a.rank, acc=not a.no_acc, gradnorm_tol=a.tol, max_iters=a.max_iters,
+    out = run(a.grid, a.agents, a.rank, range_fraction=a.range_fraction, acc=not a.no_acc, gradnorm_tol=a.tol, max_iters=a.max_iters,
               check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev)
     if rk == 0:
         print(json.dumps(out))
