@@ -113,6 +113,7 @@ SYMBOLS = {
     "dcora_problem_time_spmm": (C.c_int, [VP, C.c_int32, c_double_p, c_double_p]),
     "dcora_problem_time_kernel": (C.c_int, [VP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "dcora_debug_trsv_trace": (C.c_int, [VP, C.c_int32, c_uint8_p, C.POINTER(C.c_uint64), C.c_int32]),
+    "dcora_set_trsv_max_warps": (None, [C.c_int32]),
     "dcora_selfcheck_coupling": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.POINTER(HaloSegment), C.c_int32,
                                            c_int32_p, c_int32_p, c_double_p,

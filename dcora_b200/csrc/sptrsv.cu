@@ -19,6 +19,7 @@
 // are processed together; the panels are (factor row, r) row-major, the same memory shape
 // as every other vector.
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 
 #include "trsv_dev.cuh"
@@ -95,11 +96,19 @@ cudaError_t up(T **dst, const std::vector<T> &src) {
 
 }  // namespace
 
+// warps of the largest agents: 64 (4 CTAs x 16 warps) by default, 128 (8 CTAs) when the
+// caller expects few agents to run concurrently (dcora_set_trsv_max_warps: a colour class of
+// <= 18 agents leaves SMs idle at 4 CTAs per agent)
+static std::atomic<int> g_trsv_max_warps{64};
+void set_trsv_max_warps(int w) { g_trsv_max_warps.store(w >= 128 ? 128 : 64); }
+
 int trsv_warps_for(double rows_per_agent) {
   // enough warps to spread one agent's factor over several SMs; few for tiny
   // agents (a single CTA: the level barriers become __syncthreads)
+  static const int env = getenv("DCORA_TRSV_WARPS") ? atoi(getenv("DCORA_TRSV_WARPS")) : 0;
+  const int big = env >= 128 ? 128 : env == 64 ? 64 : g_trsv_max_warps.load();
   return rows_per_agent < 400.0 ? 8 : rows_per_agent < 1500.0 ? 16
-         : rows_per_agent < 4000.0 ? 32 : 64;
+         : rows_per_agent < 4000.0 ? 32 : rows_per_agent < 12000.0 ? 64 : big;
 }
 
 int upload_factor(DeviceMatrices *M, const std::vector<HostFactor> &HF,
@@ -228,9 +237,14 @@ static int launch_trsv_shape(dcora_problem *p, const double *V, double *T, doubl
       case 8: return launch_trsv<R, DH, 1, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 16: return launch_trsv<R, DH, 1, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 32: return launch_trsv<R, DH, 2, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
+      case 128: return launch_trsv<R, DH, 8, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       default: return launch_trsv<R, DH, 4, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
     }
   } else {
+    if (nw > 64) {
+      set_error("K5: 128-warp tapes (dcora_set_trsv_max_warps) support ranks <= 8 only");
+      return DCORA_ERR_ARG;
+    }
     switch (nw) {
       case 8: return launch_trsv<R, DH, 1, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 16: return launch_trsv<R, DH, 2, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
@@ -263,3 +277,5 @@ int launch_precond(dcora_problem *p, const double *X, const double *V, double *O
 }
 
 }  // namespace dcora
+
+extern "C" void dcora_set_trsv_max_warps(int32_t warps) { dcora::set_trsv_max_warps(warps); }

@@ -33,8 +33,11 @@ class StaircaseResult:
 
 def riemannian_staircase(problem: QuadraticProblem, X0, r_max=None, eta=1e-3,
                          params: ROptParameters | None = None, escape_tol=1e-6,
-                         certify_tol=1e-9, max_matvecs=20000) -> StaircaseResult:
-    """`problem` is the rank-r0 problem of the start X0 (r0 x K)."""
+                         certify_tol=1e-9, max_matvecs=20000,
+                         second_order_escape=False) -> StaircaseResult:
+    """`problem` is the rank-r0 problem of the start X0 (r0 x K).  `second_order_escape`: the
+    isSecondOrder flag of escapeSaddle (true in SingleRobotExample_RASLAM.cpp:272-277, the
+    centralised problem; false in the multi-robot drivers)."""
     t_start = time.perf_counter()
     params = params or ROptParameters(RTR_iterations=300, RTR_tCG_iterations=500,
                                       gradnorm_tol=1e-6, time_bound_s=0.0)
@@ -64,7 +67,8 @@ def riemannian_staircase(problem: QuadraticProblem, X0, r_max=None, eta=1e-3,
         if cert.theta >= -eta / 2:
             break
         Pn = P.with_rank(r + 1)
-        Xn, ok = Pn.escapeSaddle(X, cert.theta, v, escape_tol, escape_tol)
+        Xn, ok = Pn.escapeSaddle(X, cert.theta, v, escape_tol, escape_tol,
+                                  isSecondOrder=second_order_escape)
         if not ok:
             break
         P, X, r = Pn, Xn, r + 1

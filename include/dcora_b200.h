@@ -341,6 +341,13 @@ int dcora_problem_time_kernel(dcora_problem *p, int32_t kind, int32_t iters,
 int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, const uint8_t *active,
                            uint64_t *stamps, int32_t max_stamps);
 
+/* Warps the preconditioner solve (K5) of a large agent (>= 12000 columns) is dealt to by
+ * handles created AFTER this call: 64 (default: clusters of 4 CTAs) or 128 (clusters of 8 CTAs,
+ * ranks <= 8 only).  128 pays when at most ~18 agents are solved concurrently (small colour
+ * classes, i.e. several GPUs): the solve is a latency chain and 4 CTAs per agent would leave
+ * SMs idle. */
+void dcora_set_trsv_max_warps(int32_t warps);
+
 /* Host-only self checks of the setup code (no GPU needed, no usable result):
  * max |Y_layout - Y_csr| of the CSR -> BSR/remainder conversion on internally
  * generated X, and the relative residual of the host Cholesky factor of
