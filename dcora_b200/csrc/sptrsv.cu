@@ -100,13 +100,14 @@ cudaError_t up(T **dst, const std::vector<T> &src) {
 // caller expects few agents to run concurrently (dcora_set_trsv_max_warps: a colour class of
 // <= 18 agents leaves SMs idle at 4 CTAs per agent)
 static std::atomic<int> g_trsv_max_warps{64};
-void set_trsv_max_warps(int w) { g_trsv_max_warps.store(w >= 128 ? 128 : 64); }
+static int legal_big_warps(int w) { return w >= 256 ? 256 : w >= 128 ? 128 : w >= 96 ? 96 : 64; }
+void set_trsv_max_warps(int w) { g_trsv_max_warps.store(legal_big_warps(w)); }
 
 int trsv_warps_for(double rows_per_agent) {
   // enough warps to spread one agent's factor over several SMs; few for tiny
   // agents (a single CTA: the level barriers become __syncthreads)
   static const int env = getenv("DCORA_TRSV_WARPS") ? atoi(getenv("DCORA_TRSV_WARPS")) : 0;
-  const int big = env >= 128 ? 128 : env == 64 ? 64 : g_trsv_max_warps.load();
+  const int big = env > 0 ? legal_big_warps(env) : g_trsv_max_warps.load();
   return rows_per_agent < 400.0 ? 8 : rows_per_agent < 1500.0 ? 16
          : rows_per_agent < 4000.0 ? 32 : rows_per_agent < 12000.0 ? 64 : big;
 }
@@ -184,6 +185,9 @@ static cudaError_t trsv_set_attrs(int device, int smem_bytes) {
   if (device < 64 && (done & (1ull << device))) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL, NW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess && CL > 8)
+    e = cudaFuncSetAttribute(trsv_tape_kernel<R, DH, CL, NW>,
+                             cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e == cudaSuccess && device < 64) done |= 1ull << device;
   return e;
 }
@@ -237,12 +241,14 @@ static int launch_trsv_shape(dcora_problem *p, const double *V, double *T, doubl
       case 8: return launch_trsv<R, DH, 1, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 16: return launch_trsv<R, DH, 1, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 32: return launch_trsv<R, DH, 2, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
+      case 96: return launch_trsv<R, DH, 6, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 128: return launch_trsv<R, DH, 8, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
+      case 256: return launch_trsv<R, DH, 16, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       default: return launch_trsv<R, DH, 4, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
     }
   } else {
     if (nw > 64) {
-      set_error("K5: 128-warp tapes (dcora_set_trsv_max_warps) support ranks <= 8 only");
+      set_error("K5: tapes of more than 64 warps (dcora_set_trsv_max_warps) support ranks <= 8 only");
       return DCORA_ERR_ARG;
     }
     switch (nw) {

@@ -167,7 +167,7 @@ class RBCD:
     def __init__(self, gp: GlobalProblem, r: int, rank=0, world=1, device=0,
                  params: ROptParameters | None = None, precond=True, group=None,
                  plan: RankPlan | None = None, diag=None, acceleration=False,
-                 restart_interval=30, _problem=None):
+                 restart_interval=30, _problem=None, k5_warps=None):
         import torch
         self.torch = torch
         self.gp, self.r, self.rank, self.world, self.group = gp, r, rank, world, group
@@ -186,7 +186,27 @@ class RBCD:
             reg = None if not precond else ("auto_ra" if gp.ra else 0.1)
             agents = [AgentData(n=int(gp.n_a[a]), l=int(gp.l_a[a]), b=int(gp.b_a[a]), Q=diag[a],
                                 precond_reg=reg) for a in range(plan.a0, plan.a1)]
-            self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
+            # K5 is a latency chain per agent (261 us with 64 warps = 4 CTAs per agent, 212 us
+            # with 96, 188 us with 128, 138 us with 256 on a configs[4] agent): when the colour
+            # steps of this job solve few agents per GPU (several ranks), more CTAs per agent
+            # shorten every step and the clusters still fit the machine in one wave.  The
+            # choice follows the LARGEST class on any rank (all ranks compute the same value).
+            # (> 64 warps serves ranks <= 8: pass k5_warps=64 for a staircase that goes higher)
+            if k5_warps is None:
+                biggest = 0
+                for (b0, b1) in rank_agents(gp.A, world):
+                    loc = plan.colors[b0:b1]
+                    if len(loc):
+                        biggest = max(biggest, int(np.bincount(loc).max()))
+                k5_warps = 64
+                if r <= 8 and biggest > 0:
+                    k5_warps = 256 if biggest <= 8 else 128 if biggest <= 16 else 96 if biggest <= 24 else 64
+            from . import _lib
+            _lib.load().dcora_set_trsv_max_warps(int(k5_warps))
+            try:
+                self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
+            finally:
+                _lib.load().dcora_set_trsv_max_warps(64)
             segs = [plan.seg] * world if world > 1 else []
             self.P.set_coupling(plan.coupling, segs, row_key=plan.row_key)
         # the iterate lives in ONE device buffer (self.X) that only the library writes

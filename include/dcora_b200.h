@@ -342,10 +342,11 @@ int dcora_debug_trsv_trace(dcora_problem *p, int32_t agent, const uint8_t *activ
                            uint64_t *stamps, int32_t max_stamps);
 
 /* Warps the preconditioner solve (K5) of a large agent (>= 12000 columns) is dealt to by
- * handles created AFTER this call: 64 (default: clusters of 4 CTAs) or 128 (clusters of 8 CTAs,
- * ranks <= 8 only).  128 pays when at most ~18 agents are solved concurrently (small colour
- * classes, i.e. several GPUs): the solve is a latency chain and 4 CTAs per agent would leave
- * SMs idle. */
+ * handles created AFTER this call: 64 (default: clusters of 4 CTAs), 96 (6 CTAs), 128 (8 CTAs)
+ * or 256 (16 CTAs, non-portable cluster size); more than 64 serves ranks <= 8 only.  The solve
+ * is a latency chain per agent, so when few agents are solved concurrently (small colour
+ * classes: several GPUs) more CTAs per agent shorten it while the clusters still fit the
+ * machine in one wave (<= 24 agents at 96, <= 16 at 128, <= 8 at 256). */
 void dcora_set_trsv_max_warps(int32_t warps);
 
 /* Host-only self checks of the setup code (no GPU needed, no usable result):

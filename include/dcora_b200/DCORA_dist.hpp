@@ -606,10 +606,22 @@ class DistributedAgentBatch {
       desc[a].G = nullptr;
       desc[a].precond_reg = P.rangeAided() ? DCORA_REG_AUTO_RA : 0.1;
     }
+    // CTAs per agent of the preconditioner solve: by the largest colour class on any process
+    // (see dcora_set_trsv_max_warps and dcora_b200/rbcd.py)
+    int biggest = 0;
+    for (int rk = 0; rk < world; ++rk) {
+      const auto blk = rankAgents(A_global_, world, rk);
+      std::vector<int> cnt(plan_.num_colors + 1, 0);
+      for (int a = blk.first; a < blk.second; ++a) biggest = std::max(biggest, ++cnt[plan_.colors[a]]);
+    }
+    const int warps = (r > 8 || biggest == 0) ? 64 : biggest <= 8 ? 256 : biggest <= 16 ? 128
+                      : biggest <= 24 ? 96 : 64;
+    dcora_set_trsv_max_warps(warps);
     h_ = std::make_shared<detail::Handle>();
     DCORA_B200_CALL(dcora_problem_create(desc.data(), A, (int32_t)r, (int32_t)d_,
                                          P.rangeAided() ? DCORA_ORDER_RA : DCORA_ORDER_SE, device,
                                          &h_->p));
+    dcora_set_trsv_max_warps(64);
     std::vector<dcora_halo_segment> segs(world > 1 ? world : 0, plan_.seg);
     DCORA_B200_CALL(dcora_problem_set_coupling_keyed(
         h_->p, segs.data(), (int32_t)segs.size(), plan_.coupling.rowptr.data(),

@@ -156,3 +156,46 @@ def align_lifted_trajectory(X, Tw0, d, is_global=True):
         T[:, c:c + d] = mf.project_rotation(T[:, c:c + d])
         T[:, c + d] -= t0
     return T
+
+
+def count_below(S, sigma):
+    """Number of eigenvalues of the symmetric S below sigma (Sylvester's law of inertia on the
+    pivots of a symmetric-mode sparse LU without row exchanges, like is_psd); None if the
+    factorisation needed an off-diagonal pivot."""
+    k = S.shape[0]
+    M = (S - sigma * sp.identity(k)).tocsc()
+    try:
+        lu = spla.splu(M, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0,
+                       options=dict(SymmetricMode=True))
+    except RuntimeError:
+        return None
+    if not np.array_equal(lu.perm_r, lu.perm_c):
+        return None
+    return int(np.sum(lu.U.diagonal() < 0))
+
+
+def lambda_min_bisect(S, rel=1e-3, floor=1e-7):
+    """lambda_min(S) for large S without trusting a Krylov iteration to find the right end of
+    a clustered spectrum: bracket it by inertia counts, bisect to a relative width `rel`, then
+    one shift-invert Lanczos step from the lower end of the bracket (nearest eigenvalue above
+    it = lambda_min).  Returns (lambda_min, v)."""
+    lo, hi = -1e-3, 1e-3
+    while True:
+        c = count_below(S, lo)
+        if c == 0:
+            break
+        hi, lo = lo, lo * 4.0
+    while (count_below(S, hi) or 0) == 0:
+        lo, hi = hi, hi * 4.0
+    while hi - lo > max(rel * max(abs(lo), abs(hi)), floor):
+        mid = 0.5 * (lo + hi)
+        c = count_below(S, mid)
+        if c is None:
+            mid = lo + 0.37 * (hi - lo)
+            c = count_below(S, mid)
+        if c == 0:
+            lo = mid
+        else:
+            hi = mid
+    w, v = spla.eigsh(S.tocsc(), k=1, sigma=lo - 0.1 * (hi - lo) - 1e-12, which="LM", tol=1e-12)
+    return float(w[0]), v[:, 0]

@@ -6,7 +6,8 @@ Follows examples/SingleRobotExample_RASLAM.cpp:182-283: from r = d, optimize (RT
 example's 200 x 200 iterations, gradnorm_tol 1e-4) -> dual certificate S = Q - Lambda ->
 fastVerification(eta = 1e-4) -> escapeSaddle to rank r + 1, until S + eta I is PSD.  The
 start is the data file's ground truth lifted with [I; 0] (the example's non-odometry branch:
-deterministic, unlike its random landmarks).  The optimisation runs on oracle/native (C++ -O3
+deterministic, unlike its random landmarks).  lambda_min and the escape direction come from
+certify.lambda_min_bisect (inertia counts + shift-invert).  The optimisation runs on oracle/native (C++ -O3
 restatement of the same RTR/tCG, cross-checked against oracle/solver.py in
 tests/test_oracle_native.py); certificate, eigenvalue and escape on the scipy oracle.
 Writes the per-level record and the final answer to tests/golden/expected.json["tiers_staircase"].
@@ -30,16 +31,6 @@ TOL = 1e-4          # gradnorm_tol, gradient_tolerance, preconditioned_gradient_
 R_MAX = 8
 
 
-def tight_lambda_min(S, psd, theta):
-    """lambda_min(S) by shift-invert Lanczos: the eigenvalue nearest to a shift placed just
-    below the spectrum (PSD case: below -eta, which bounds it; otherwise 5 % below the
-    spectrum-shift estimate theta of fastVerification)."""
-    import scipy.sparse.linalg as spla
-    sigma = -2.0 * ETA if psd else theta - 0.05 * abs(theta)
-    w = spla.eigsh(S.tocsc(), k=1, sigma=sigma, which="LM", tol=1e-12, return_eigenvectors=False)
-    return float(w[0])
-
-
 def main():
     meas, info = load_golden("tiers")
     d = info["d"]
@@ -57,18 +48,22 @@ def main():
             X = mf.project_manifold(L, X)
         t0 = time.time()
         cache = f"/tmp/tiers_level_r{r}.npy"
+        prob = native.AgentProblem(L, Q, reg)
         if os.path.exists(cache) and os.environ.get("TIERS_RESUME"):
             Xopt, st = np.load(cache), dict(outer=-1, inner=-1)     # resumed run (same input)
         else:
-            prob = native.AgentProblem(L, Q, reg)
             Xopt, st = prob.update(np.zeros((r, L.k), order="F"), np.asfortranarray(X),
                                    max_outer=200, max_inner=200, tol=TOL, delta0=100.0)
         P = solver.QuadraticProblem(L, Q, precond_reg=reg)
         f, gn = P.f(Xopt), P.rgrad_norm(Xopt)
         np.save(f"/tmp/tiers_level_r{r}.npy", Xopt)
         S = certify.certificate_matrix(L, Xopt, Q)
-        psd, theta, v = certify.fast_verification(S, ETA)
-        lam = tight_lambda_min(S, psd, theta)
+        # fastVerification's verdict (PSD test of S + eta I by factorisation); the eigenpair by
+        # inertia bisection + shift-invert instead of the reference's spectrum-shifted Lanczos,
+        # which needs > 30 minutes here when lambda_min sits in the cluster around zero
+        psd = certify.is_psd((S + ETA * __import__("scipy.sparse").sparse.identity(L.k)).tocsr())
+        lam, v = certify.lambda_min_bisect(S)
+        theta = None if psd else float(v @ (S @ v))
         lev = dict(r=r, fOpt=f, gradNormOpt=gn, outer=int(st["outer"]), inner=int(st["inner"]),
                    is_psd=bool(psd), lambda_min=lam, theta=None if theta is None else float(theta),
                    seconds=time.time() - t0)
@@ -83,13 +78,31 @@ def main():
         if not ok:
             print("escape failed", flush=True)
             break
+    # polish: the level loop stops after 200 RTR iterations like the example, possibly above the
+    # gradient tolerance; the known answer the GPU arm is compared with is the CONVERGED optimum
+    # of the certified rank (path independent): more RTR iterations from the certified point
+    fin = levels[-1]
+    polished = None
+    if fin["is_psd"]:
+        t0 = time.time()
+        Xp = Xopt
+        for _ in range(10):
+            Xp, st = prob.update(np.zeros((r, L.k), order="F"), np.asfortranarray(Xp),
+                                 max_outer=500, max_inner=500, tol=1e-6, delta0=100.0)
+            if P.rgrad_norm(Xp) < 1e-5:
+                break
+        Sp = certify.certificate_matrix(L, Xp, Q)
+        lam_p, _ = certify.lambda_min_bisect(Sp)
+        polished = dict(fOpt=P.f(Xp), gradNormOpt=P.rgrad_norm(Xp), lambda_min=lam_p,
+                        is_psd=bool(lam_p + ETA > 0), seconds=time.time() - t0)
+        print("polished", polished, flush=True)
     path = os.path.join(HERE, "expected.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
-    fin = levels[-1]
     out["tiers_staircase"] = dict(init="gt", eta=ETA, gradnorm_tol=TOL, RTR_iterations=200,
                                   RTR_tCG_iterations=200, r_min=d, levels=levels,
                                   certified=fin["is_psd"], rank=fin["r"], fOpt=fin["fOpt"],
                                   cost_2f=2 * fin["fOpt"], lambda_min=fin["lambda_min"],
+                                  polished=polished,
                                   oracle_seconds=time.time() - t_all)
     with open(path, "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)

@@ -1,8 +1,6 @@
 #!/bin/bash
-# K5 slot trace with 64- and 128-warp tapes + ncu --set full of the 64-warp kernel
+# K5 slot trace with tapes of 64 / 96 / 128 / 256 warps per agent
 OUT=gpurun_out/${1:-k5w}; mkdir -p $OUT
-python tools/trsv_trace.py > $OUT/trace64.txt 2>&1; grep total $OUT/trace64.txt
-DCORA_TRSV_WARPS=128 python tools/trsv_trace.py > $OUT/trace128.txt 2>&1; grep total $OUT/trace128.txt; tail -3 $OUT/trace128.txt | cut -c1-300
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:trsv_tape_kernel \
-  -o $OUT/k5 -f python tools/trsv_trace.py > $OUT/ncu.log 2>&1
-tail -3 $OUT/ncu.log; ls -la $OUT
+for w in 64 96 128 256; do
+  DCORA_TRSV_WARPS=$w timeout 300 python tools/trsv_trace.py > $OUT/trace_w$w.txt 2>&1; echo "== $w warps"; grep total $OUT/trace_w$w.txt; tail -2 $OUT/trace_w$w.txt | cut -c1-200
+done
