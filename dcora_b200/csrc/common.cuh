@@ -234,6 +234,11 @@ struct dcora_problem {
   int *flags = nullptr;            // per-agent int flags (device)
   int *h_flags = nullptr;          // pinned mirror
   cudaEvent_t count_ev[dcora::DCORA_COUNT_RING] = {};  // read-back events of the count ring (solver.cu)
+  // certificate workspace, kept across dcora_certify calls (certify.cu): one arena for the
+  // Krylov bases and the rank-1 twin of this handle that applies Q to single vectors
+  double *cert_ws = nullptr;
+  size_t cert_ws_len = 0;
+  dcora_problem *cert_q1 = nullptr;
   double *vec(int i);              // lazily allocated workspace vector i
   ~dcora_problem();
 };

@@ -170,6 +170,8 @@ dcora_problem::~dcora_problem() {
   cudaFree(G); cudaFree(stage); cudaFree(xe); cudaFree(hstage); cudaFree(pack_idx); cudaFree(partials); cudaFree(scal); cudaFree(flags);
   cudaFreeHost(h_scal); cudaFreeHost(h_flags);
   for (cudaEvent_t e : count_ev) if (e) cudaEventDestroy(e);
+  cudaFree(cert_ws);
+  delete cert_q1;
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
 
