@@ -318,7 +318,7 @@ def run_ours(args):
                                 log=None, dist_rank=rank, world=world, device=local_rank)
             barrier()
             ttc["levels"] = [{k: v for k, v in lv.items() if k in
-                              ("r", "sweeps", "gradnorm", "lambda_min", "is_psd", "solve_s", "certify_s")}
+                              ("r", "sweeps", "gradnorm", "lambda_min", "residual", "is_psd", "converged", "solve_s", "certify_s")}
                              for lv in ttc["levels"]]
             log(f"time-to-certified ({ttc['poses']} poses, {ttc['agents']} agents): "
                 f"{ttc['seconds']:.2f} s, certified={ttc['certified']} rank={ttc['rank']} "

@@ -205,7 +205,12 @@ def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
         Vp = t.zeros((K, r), dtype=f64, device=dev)
         Vp[:, 0] = v
         theta = float(allsum((times_S(Vp)[:, 0] * v).sum().reshape(1)))
-        return DistCertificate(is_psd=(lam + eta > 0.0), lambda_min=lam, residual=resid,
+        # Verdict: `lam` is an upper bound of lambda_min(S).  Below -eta it proves "not PSD"
+        # whether or not the iteration converged; "PSD" is only reported from a CONVERGED
+        # smallest Ritz pair whose residual leaves a margin (there is no global factorisation
+        # of the partitioned S to run the reference's exact test on)
+        psd = bool(conv and lam + eta > 0.0 and lam - resid + eta > 0.0)
+        return DistCertificate(is_psd=psd, lambda_min=lam, residual=resid,
                                iterations=it, products=nprod, converged=conv, theta=theta, v=v)
     finally:
         # restore the linear term of the RBCD state and re-arm the tracking

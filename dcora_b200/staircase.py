@@ -126,7 +126,7 @@ def escape_distributed(S_next, X_dev, v_dev, theta, gradient_tolerance,
 
 
 def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, max_iters=1000,
-                   check_every=5, certify_tol=1e-7, escape_tol=1e-4, round_solution=False,
+                   check_every=5, certify_tol=1e-8, escape_tol=1e-4, round_solution=False,
                    log=None) -> StaircaseResult:
     """Distributed Riemannian staircase on an RBCD state `S` (dcora_b200.rbcd.RBCD of any world
     size; every rank calls this collectively).  The drivers' defaults: RGradNormTol 0.1,
@@ -161,7 +161,7 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
         cert = certify_distributed(S, eta, tol=certify_tol)
         t2 = time.perf_counter()
         levels.append(dict(r=r, f=f, gradnorm=gn, sweeps=sweeps, is_psd=bool(cert.is_psd),
-                           lambda_min=cert.lambda_min, theta=cert.theta,
+                           lambda_min=cert.lambda_min, theta=cert.theta, residual=cert.residual,
                            products=cert.products, converged=bool(cert.converged),
                            solve_s=t1 - t0, certify_s=t2 - t1))
         if log:
