@@ -57,8 +57,9 @@ combine_f_kernel(const int *list, const int *agent_chunk0, const double *partial
 __global__ void __launch_bounds__(128)
 rtr_init_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
                 double *scal, double tol, double delta0, double max_delta,
-                int *counter) {
+                int *counter, int *counter_next) {
   __shared__ double sm[4];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter_next = 0;   // the next counting kernel's slot
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   const double gg = agent_sum(agent_chunk0, partials, a, 0, sm);
   if (threadIdx.x != 0) return;
@@ -133,8 +134,10 @@ tcg_stepA_kernel(const int *list, const int *agent_chunk0, const double *partial
 // partial 0 = <r, r> after the update
 __global__ void __launch_bounds__(128)
 tcg_stepB_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
-                 double *scal, int j, int min_inner, int max_inner, int *counter) {
+                 double *scal, int j, int min_inner, int max_inner, int *counter,
+                 int *counter_next) {
   __shared__ double sm[4];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter_next = 0;
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_STEP] == 0) return;
@@ -218,8 +221,9 @@ rtr_rho_kernel(const int *list, const int *agent_chunk0, const double *partials,
 // after the gradient at the accepted point: partial 0 = <gf, gf>
 __global__ void __launch_bounds__(128)
 rtr_accept_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
-                  double *scal, int max_iter, int single_mode, int *counter) {
+                  double *scal, int max_iter, int single_mode, int *counter, int *counter_next) {
   __shared__ double sm[4];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter_next = 0;
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_OUTER] == 0) return;
@@ -269,15 +273,22 @@ struct CountRing {
   dcora_problem *p;
   int *dev, *host;
   int next = 0;
+  bool fresh = true;
   explicit CountRing(dcora_problem *p_)
       : p(p_), dev(p_->flags + (size_t)NF * p_->M->A + 4),
         host(p_->h_flags + (size_t)NF * p_->M->A + 4) {}
-  // a zeroed slot for the next counting kernel
-  int open(int **dptr) {
+  // a zeroed slot for the next counting kernel: the first one is cleared here, every later
+  // one by the counting kernel before it (*dnext; its previous read-back was enqueued
+  // DCORA_COUNT_RING - 1 counting kernels earlier on the same stream)
+  int open(int **dptr, int **dnext) {
     const int s = next;
     next = (next + 1) % DCORA_COUNT_RING;
-    if (cudaMemsetAsync(dev + s, 0, sizeof(int), p->stream) != cudaSuccess) return -1;
+    if (fresh) {
+      if (cudaMemsetAsync(dev + s, 0, sizeof(int), p->stream) != cudaSuccess) return -1;
+      fresh = false;
+    }
     *dptr = dev + s;
+    *dnext = dev + next;
     return s;
   }
   // after the counting kernel: start the read-back
@@ -454,12 +465,12 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
   const int single_mode = prm->RTR_iterations == 1;
   const int max_outer = single_mode ? 12 : prm->RTR_iterations;
   const double Delta0 = prm->RTR_initial_radius;
-  int *dcnt = nullptr;
-  int outer_slot = ring.open(&dcnt);
+  int *dcnt = nullptr, *dnext = nullptr;
+  int outer_slot = ring.open(&dcnt, &dnext);
   if (outer_slot < 0) return DCORA_ERR_CUDA;
   rtr_init_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
                                             p->scal, prm->gradnorm_tol, Delta0,
-                                            single_mode ? Delta0 : 5.0 * Delta0, dcnt);
+                                            single_mode ? Delta0 : 5.0 * Delta0, dcnt, dnext);
   DCORA_LAUNCH_CHECK(p);
   DCORA_TRY(ring.post(outer_slot));
   pt.mark(0);
@@ -500,10 +511,10 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
       DCORA_LAUNCH_CHECK(p);
       // eta += c delta, Heta += c Hd, r += c_r Hd and <r, r> in one pass
       DCORA_TRY(launch_tcg_update(p, S_CETA, S_CR, delta, Hd, eta, Heta, r, F_STEP));
-      const int slot = ring.open(&dcnt);
+      const int slot = ring.open(&dcnt, &dnext);
       if (slot < 0) return DCORA_ERR_CUDA;
       tcg_stepB_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags,
-                                                 p->scal, j, 0, prm->RTR_tCG_iterations, dcnt);
+                                                 p->scal, j, 0, prm->RTR_tCG_iterations, dcnt, dnext);
       DCORA_LAUNCH_CHECK(p);
       DCORA_TRY(ring.post(slot));
       pt.mark(2);
@@ -536,10 +547,10 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     pt.mark(4);
     DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));
     DCORA_TRY(gradient_at(p, x1, EG, gf, S, F_ACCEPT, xq));
-    outer_slot = ring.open(&dcnt);
+    outer_slot = ring.open(&dcnt, &dnext);
     if (outer_slot < 0) return DCORA_ERR_CUDA;
     rtr_accept_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
-                                                max_outer, single_mode, dcnt);
+                                                max_outer, single_mode, dcnt, dnext);
     DCORA_LAUNCH_CHECK(p);
     DCORA_TRY(ring.post(outer_slot));
     pt.mark(5);

@@ -237,6 +237,13 @@ static int launch_trsv_shape(dcora_problem *p, const double *V, double *T, doubl
                              int trace_agent) {
   const int nw = p->M->F.nwarps;
   if constexpr (R <= 8) {
+    // 64 warps run as 8 CTAs x 8 warps (up to two CTAs per SM) rather than 4 x 16: the walk is
+    // bound by LSU wavefronts per SM, and the smaller CTAs spread a solve over twice the SMs
+    // whenever fewer than a full colour class is active (212 vs 266 us for one agent alone,
+    // equal for 28 agents; 33.2 vs 34.9 ms per RBCD iteration).  DCORA_K5_CL8=0: 4 x 16.
+    static const bool cl8 = !(getenv("DCORA_K5_CL8") && atoi(getenv("DCORA_K5_CL8")) == 0);
+    if (cl8 && nw == 64)
+      return launch_trsv<R, DH, 8, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
     switch (nw) {
       case 8: return launch_trsv<R, DH, 1, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 16: return launch_trsv<R, DH, 1, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);

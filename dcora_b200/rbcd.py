@@ -178,10 +178,21 @@ class RBCD:
             self.plan = plan
             self.P = _problem
         else:
+            import os, sys, time
+            timing = os.environ.get("DCORA_SETUP_TIMING") and rank == 0
+            t_lap = [time.perf_counter()]
+
+            def lap(what):
+                if timing:
+                    now = time.perf_counter()
+                    print(f"[dcora setup] {what:28s} {now - t_lap[0]:8.3f} s (python)", file=sys.stderr)
+                    t_lap[0] = now
             if plan is None or diag is None:
                 blocks = rank_agents(gp.A, world)
                 diag, cross = gp.split(agents=range(*blocks[rank]))
+                lap("split of Q by agent")
                 plan = make_plans(gp, world, cross)[rank]
+                lap("exchange plans + colouring")
             self.plan = plan
             reg = None if not precond else ("auto_ra" if gp.ra else 0.1)
             agents = [AgentData(n=int(gp.n_a[a]), l=int(gp.l_a[a]), b=int(gp.b_a[a]), Q=diag[a],
@@ -207,8 +218,10 @@ class RBCD:
                 self.P = QuadraticProblem(agents, r, gp.d, ORDER_RA if gp.ra else ORDER_SE, device)
             finally:
                 _lib.load().dcora_set_trsv_max_warps(64)
+            lap("dcora_problem_create (total)")
             segs = [plan.seg] * world if world > 1 else []
             self.P.set_coupling(plan.coupling, segs, row_key=plan.row_key)
+            lap("set_coupling")
         # the iterate lives in ONE device buffer (self.X) that only the library writes
         self.P.set_iterate_tracking(True)
         self.params = params or ROptParameters()
