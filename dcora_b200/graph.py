@@ -288,22 +288,34 @@ class GlobalProblem:
         `cross` = scipy CSR (K x K) holding only the entries that couple
         different agents."""
         Q = self.Q()
-        aoc = self.agent_of_col().astype(np.int32)
-        row_agent = np.repeat(aoc, np.diff(Q.indptr))
-        same = aoc[Q.indices] == row_agent
-        csum = np.concatenate([[0], np.cumsum(same, dtype=np.int64)])
-        dptr = csum[Q.indptr]
-        dcol = (Q.indices - self.coff[row_agent].astype(Q.indices.dtype))[same]
-        dval = Q.data[same]
+        want = set(range(self.A)) if agents is None else set(int(a) for a in agents)
+        indptr, indices, data = Q.indptr, Q.indices, Q.data
+        # agents own contiguous column ranges: an entry of a row of agent a is "same" iff its
+        # column lies in [coff[a], coff[a+1]).  One pass per agent over its own rows (cache
+        # sized pieces, no K- or nnz-sized gathers).
+        xcount = np.empty(self.K, np.int64)
+        xi, xd = [], []
         diag = {}
-        for a in (range(self.A) if agents is None else agents):
-            c0, c1 = self.coff[a], self.coff[a + 1]
-            p0, p1 = dptr[c0], dptr[c1]
-            diag[a] = ((dptr[c0:c1 + 1] - p0).astype(np.int32),
-                       np.ascontiguousarray(dcol[p0:p1], dtype=np.int32),
-                       np.ascontiguousarray(dval[p0:p1]))
-        xptr = (np.arange(len(csum)) - csum)[Q.indptr]
-        cross = sp.csr_matrix((Q.data[~same], Q.indices[~same], xptr), shape=Q.shape)
+        for a in range(self.A):
+            c0, c1 = int(self.coff[a]), int(self.coff[a + 1])
+            p0, p1 = int(indptr[c0]), int(indptr[c1])
+            idx = indices[p0:p1]
+            same = (idx >= c0) & (idx < c1)
+            ptr = indptr[c0:c1 + 1] - p0
+            csum = np.concatenate([[0], np.cumsum(same, dtype=np.int64)])
+            dptr = csum[ptr]
+            xcount[c0:c1] = np.diff(ptr) - np.diff(dptr)
+            other = ~same
+            xi.append(idx[other])
+            xd.append(data[p0:p1][other])
+            if a in want:
+                diag[a] = (dptr.astype(np.int32),
+                           np.ascontiguousarray(idx[same] - c0, dtype=np.int32),
+                           np.ascontiguousarray(data[p0:p1][same]))
+        xptr = np.concatenate([[0], np.cumsum(xcount)])
+        cross = sp.csr_matrix((np.concatenate(xd) if xd else np.zeros(0),
+                               np.concatenate(xi) if xi else np.zeros(0, indices.dtype),
+                               xptr.astype(indptr.dtype)), shape=Q.shape)
         return diag, cross
 
     def agent_graph(self, cross=None):
