@@ -244,6 +244,13 @@ static int launch_trsv_shape(dcora_problem *p, const double *V, double *T, doubl
     static const bool cl8 = !(getenv("DCORA_K5_CL8") && atoi(getenv("DCORA_K5_CL8")) == 0);
     if (cl8 && nw == 64)
       return launch_trsv<R, DH, 8, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
+    // the same for the larger shapes (non-portable cluster sizes 12 / 16): one agent alone
+    // 171 vs 212 us at 96 warps, 148 vs 189 us at 128 warps (profiles/r02_k5_cta_shape_big.txt)
+    const bool cl8big = cl8;
+    if (cl8big && nw == 96)
+      return launch_trsv<R, DH, 12, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
+    if (cl8big && nw == 128)
+      return launch_trsv<R, DH, 16, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
     switch (nw) {
       case 8: return launch_trsv<R, DH, 1, 8>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
       case 16: return launch_trsv<R, DH, 1, 16>(p, V, T, X, OUT, mask_flag, trace, trace_agent);
