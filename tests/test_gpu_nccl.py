@@ -84,3 +84,65 @@ def test_two_ranks_are_bit_identical_to_one_rank(acc):
             assert abs(f2 - f1) <= 1e-9 * abs(f1) and abs(g2 - g1) <= 1e-9 * g1
     assert np.array_equal(got, X1)
     assert hist1[-1][0] < hist1[0][0]
+
+
+def _stair_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                                world_size=world, device_id=torch.device("cuda", rank))
+        q.put((rank,) + _staircase(rank, world))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, None, traceback.format_exc(), repr(e)))
+
+
+def _staircase(rank, world):
+    import dcora_b200 as dc
+    from dcora_b200 import rbcd
+    from dcora_b200.staircase import rbcd_staircase
+    from oracle import manifold as mf
+    from tests.common import central_problem
+    from tests.test_gpu_rbcd import _setup
+    gp, blocks, cross = _setup("smallGrid3D", 5, 3)
+    G = rbcd.RBCD(gp, 3, rank=rank, world=world, device=rank,
+                  params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=1e-9,
+                                           RTR_iterations=10, RTR_tCG_iterations=100))
+    X0 = mf.random_point(central_problem("smallGrid3D", 3)[0].L, np.random.default_rng(7))
+    res = rbcd_staircase(G, X0, r_max=7, eta=1e-3, gradnorm_tol=1e-4, max_iters=800,
+                         check_every=10, certify_tol=1e-9)
+    return (res.certified, res.rank, res.cost, res.lambda_min,
+            [(lv["r"], lv["is_psd"]) for lv in res.levels])
+
+
+def test_two_rank_staircase_escapes_and_certifies_like_one_rank():
+    # RBCD -> distributed certificate -> distributed escapeSaddle -> next rank with the agents
+    # dealt to 2 processes: same levels, same certified optimum as on one process
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stair_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    one = _staircase(0, 1)
+    assert one[0] and abs(2 * one[2] - 1025.3980521) < 1e-4
+    for r in res:
+        assert r[1] is not None, f"rank {r[0]}: {r[2]}"
+        certified, rank_, cost, lam, levels = r[1:]
+        assert certified and rank_ == one[1] and levels == one[4]
+        assert abs(cost - one[2]) <= 1e-8 * abs(one[2])
+        assert lam > -1e-3
