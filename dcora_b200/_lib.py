@@ -114,6 +114,9 @@ SYMBOLS = {
     "dcora_problem_time_kernel": (C.c_int, [VP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "dcora_debug_trsv_trace": (C.c_int, [VP, C.c_int32, c_uint8_p, C.POINTER(C.c_uint64), C.c_int32]),
     "dcora_set_trsv_max_warps": (None, [C.c_int32]),
+    "dcora_selfcheck_cholesky_threads": (C.c_int, [C.c_int32, c_int32_p, c_int32_p, c_double_p,
+                                                   C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                                   c_double_p, C.POINTER(C.c_int64)]),
     "dcora_selfcheck_coupling": (C.c_int, [C.POINTER(AgentDesc), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.POINTER(HaloSegment), C.c_int32,
                                            c_int32_p, c_int32_p, c_double_p,

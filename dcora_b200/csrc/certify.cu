@@ -563,7 +563,8 @@ extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
     auto factor_shifted = [&](double sigma) {     // is S + sigma I positive definite?
       for (int i = 0; i < k; ++i) Ax[shift_pos[i]] = sigma;
       Fs = HostFactor();
-      return sparse_cholesky(k, Ap, Ai, Ax, dhh, np, &Fs) == DCORA_OK;
+      return sparse_cholesky(k, Ap, Ai, Ax, dhh, np, &Fs, DCORA_ORDERING_ND, TRSV_LEAF_ROWS,
+                             setup_threads()) == DCORA_OK;
     };
     auto times_S = [&](const std::vector<double> &x, std::vector<double> &y) {
       for (int i = 0; i < k; ++i) {

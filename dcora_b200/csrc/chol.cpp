@@ -8,7 +8,12 @@
 // is built once per (agent, Q) and applied on the device by level-scheduled
 // sparse triangular solves (sptrsv.cu).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
+#include <thread>
 #include <numeric>
 #include <queue>
 #include <set>
@@ -309,9 +314,17 @@ void nested_dissection(int n, const std::vector<std::vector<int>> &adj,
 
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
                     const std::vector<double> &Ax, int dh, int npose,
-                    HostFactor *out, int ordering, int leaf_rows) {
+                    HostFactor *out, int ordering, int leaf_rows, int threads) {
   HostFactor &F = *out;
   F.k = k;
+  const bool timing = std::getenv("DCORA_CHOL_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[chol] %-22s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
   // ---- supervariable graph
   const int npc = dh * npose;
   const int nsv = npose + (k - npc);
@@ -372,6 +385,7 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
   std::vector<int> pinv(k);
   for (int i = 0; i < k; ++i) pinv[F.perm[i]] = i;
 
+  lap("ordering");
   // ---- C = upper triangle of P A P^T in CSC (column j holds rows i <= j)
   std::vector<int> Cp(k + 1, 0);
   for (int c = 0; c < k; ++c)
@@ -390,6 +404,7 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
         if (i <= j) { Ci[fill[j]] = i; Cx[fill[j]] = Ax[p]; fill[j]++; }
       }
   }
+  lap("permute");
   // ---- elimination tree (Liu)
   std::vector<int> parent(k, -1), ancestor(k, -1);
   for (int j = 0; j < k; ++j)
@@ -420,45 +435,117 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
   const int64_t nnzL = F.Lp[k];
   F.Li.assign(nnzL, 0);
   F.Lx.assign(nnzL, 0.0);
-  // ---- numeric up-looking factorisation (row k of L from rows < k)
-  std::vector<int> cfill(F.Lp.begin(), F.Lp.end() - 1), stack(k), pattern(k);
-  std::vector<double> x(k, 0.0);
-  std::fill(flag.begin(), flag.end(), -1);
-  for (int j = 0; j < k; ++j) {
-    // pattern of row j = reach of column j's upper entries in the etree,
-    // produced in topological order (cs_ereach)
+  lap("etree + symbolic");
+  // ---- numeric up-looking factorisation (row j of L from rows < j).  Row j only reads and
+  // appends to the columns of its elimination-tree descendants, so disjoint subtrees are
+  // independent: with `threads` > 1 the tree is cut into subtrees that are factored
+  // concurrently (every row still sees the same operands in the same order: the factor is
+  // bit-identical to the serial one), then the rows above the cut follow in order.
+  std::vector<int> cfill(F.Lp.begin(), F.Lp.end() - 1);
+  std::atomic<int> failed{0};
+  struct Work {
+    std::vector<int> flag, stack, pattern;
+    std::vector<double> x;
+    explicit Work(int n) : flag(n, -1), stack(n), pattern(n), x(n, 0.0) {}
+  };
+  auto do_row = [&](int j, Work &W) {
     int top = k;
-    flag[j] = j;
+    W.flag[j] = j;
     double d = 0.0;
     for (int p = Cp[j]; p < Cp[j + 1]; ++p) {
       int i = Ci[p];
       if (i == j) { d += Cx[p]; continue; }
-      x[i] += Cx[p];   // += : tolerate duplicate entries
+      W.x[i] += Cx[p];   // += : tolerate duplicate entries
       int len = 0;
-      while (flag[i] != j) {
-        stack[len++] = i;
-        flag[i] = j;
+      while (W.flag[i] != j) {
+        W.stack[len++] = i;
+        W.flag[i] = j;
         i = parent[i];
       }
-      while (len > 0) pattern[--top] = stack[--len];
+      while (len > 0) W.pattern[--top] = W.stack[--len];
     }
     for (; top < k; ++top) {
-      const int i = pattern[top];
-      const double lji = x[i] / F.Lx[F.Lp[i]];  // L(j,i) = x_i / L(i,i)
-      x[i] = 0.0;
-      for (int p = F.Lp[i] + 1; p < cfill[i]; ++p) x[F.Li[p]] -= F.Lx[p] * lji;
+      const int i = W.pattern[top];
+      const double lji = W.x[i] / F.Lx[F.Lp[i]];  // L(j,i) = x_i / L(i,i)
+      W.x[i] = 0.0;
+      for (int p = F.Lp[i] + 1; p < cfill[i]; ++p) W.x[F.Li[p]] -= F.Lx[p] * lji;
       d -= lji * lji;
       const int q = cfill[i]++;
       F.Li[q] = j;
       F.Lx[q] = lji;
     }
-    if (!(d > 0.0) || !std::isfinite(d)) {
-      set_error("sparse_cholesky: matrix is not positive definite");
-      return DCORA_ERR_FACTOR;
-    }
+    if (!(d > 0.0) || !std::isfinite(d)) { failed.store(1); d = 1.0; }
     const int q = cfill[j]++;
     F.Li[q] = j;
     F.Lx[q] = std::sqrt(d);
+  };
+  if (threads <= 1 || k < 4000) {
+    Work W(k);
+    for (int j = 0; j < k && !failed.load(); ++j) do_row(j, W);
+  } else {
+    // subtree work = sum of colcount^2 (flops of the rows appended to a column)
+    std::vector<double> work(k);
+    for (int j = 0; j < k; ++j) work[j] = (double)colcount[j] * colcount[j];
+    for (int j = 0; j < k; ++j) if (parent[j] >= 0) work[parent[j]] += work[j];
+    std::vector<std::vector<int>> children(k);
+    std::vector<int> roots;
+    for (int j = 0; j < k; ++j) (parent[j] >= 0 ? children[parent[j]] : roots).push_back(j);
+    // cut: repeatedly open the heaviest subtree until there are enough pieces
+    std::vector<int> pieces = roots, above;
+    // (a dense separator is a chain in the tree: keep descending until the heaviest piece is
+    // a fair share of the total)
+    double total_work = 0.0;
+    for (int t : roots) total_work += work[t];
+    const double fair = total_work / (4.0 * threads);
+    for (;;) {
+      size_t h = 0;
+      for (size_t t = 1; t < pieces.size(); ++t) if (work[pieces[t]] > work[pieces[h]]) h = t;
+      const int top_node = pieces[h];
+      if (work[top_node] <= fair || children[top_node].empty()) break;
+      pieces.erase(pieces.begin() + h);
+      above.push_back(top_node);
+      for (int c : children[top_node]) pieces.push_back(c);
+    }
+    std::vector<int> piece_of(k, -1);
+    for (size_t t = 0; t < pieces.size(); ++t) piece_of[pieces[t]] = (int)t;
+    // nodes in descending order: a node inherits its parent's piece (parents have larger indices)
+    for (int j = k - 1; j >= 0; --j)
+      if (piece_of[j] < 0 && parent[j] >= 0) piece_of[j] = piece_of[parent[j]];
+    for (int a : above) piece_of[a] = -1;
+    std::vector<std::vector<int>> rows(pieces.size());
+    for (int j = 0; j < k; ++j) if (piece_of[j] >= 0) rows[piece_of[j]].push_back(j);
+    std::vector<size_t> order(pieces.size());
+    for (size_t t = 0; t < order.size(); ++t) order[t] = t;
+    std::sort(order.begin(), order.end(),
+              [&](size_t a, size_t b) { return work[pieces[a]] > work[pieces[b]]; });
+    if (timing) {
+      double wa = 0.0, wp = 0.0, wmax = 0.0;
+      for (int a : above) wa += (double)colcount[a] * colcount[a];
+      for (int t : pieces) { wp += work[t]; wmax = std::max(wmax, work[t]); }
+      std::fprintf(stderr, "[chol] %zu pieces (work %.3g, largest %.3g), %zu rows above the cut (work %.3g)\n",
+                   pieces.size(), wp, wmax, above.size(), wa);
+    }
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      Work W(k);
+      for (;;) {
+        const size_t t = next.fetch_add(1);
+        if (t >= order.size() || failed.load()) break;
+        for (int j : rows[order[t]]) do_row(j, W);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &th : pool) th.join();
+    std::sort(above.begin(), above.end());
+    Work W(k);
+    for (int j : above) { if (failed.load()) break; do_row(j, W); }
+  }
+  lap("numeric");
+  if (failed.load()) {
+    set_error("sparse_cholesky: matrix is not positive definite");
+    return DCORA_ERR_FACTOR;
   }
   F.nnz = nnzL;
   return DCORA_OK;

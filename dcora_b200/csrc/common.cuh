@@ -129,7 +129,7 @@ struct HostFactor {
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
                     const std::vector<double> &Ax, int dh, int npose,
                     HostFactor *out, int ordering = DCORA_ORDERING_ND,
-                    int leaf_rows = TRSV_LEAF_ROWS);
+                    int leaf_rows = TRSV_LEAF_ROWS, int threads = 1);
 
 double lambda_max_lanczos(int k, const int *Ap, const int *Ai, const double *Ax,
                           double tol, int max_steps);

@@ -319,6 +319,8 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       tape_warps = std::max(tape_warps, trsv_warps_for((double)(H.coff[a + 1] - H.coff[a])));
     std::vector<int> rcs(num_agents, DCORA_OK);
     const int dh = d + 1;
+    // few large agents: the spare cores factor independent elimination-tree subtrees of an agent
+    const int chol_threads = std::max(1, setup_threads() / std::max(1, num_agents));
 #pragma omp parallel for schedule(dynamic, 1) num_threads(setup_threads())
     for (int a = 0; a < num_agents; ++a) {
       const dcora_agent_desc &g = agents[a];
@@ -356,7 +358,8 @@ int dcora_problem_create(const dcora_agent_desc *agents, int32_t num_agents,
       // symmetrise numerically: P <- (P + P^T)/2 is implied by using the upper
       // triangle only inside sparse_cholesky (as CHOLMOD does for symmetric
       // input).
-      rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a]);
+      rcs[a] = sparse_cholesky(k, Ap, Ai, Ax, dh, g.n, &HF[a], DCORA_ORDERING_ND, TRSV_LEAF_ROWS,
+                               chol_threads);
       if (rcs[a] == DCORA_OK) {
         rcs[a] = build_agent_tape(HF[a], dh, trsv_warps_for((double)k), tape_warps, c0, &AT[a]);
         // only nnz(L) and the permutation are needed from here on

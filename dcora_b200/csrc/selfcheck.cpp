@@ -165,6 +165,30 @@ extern "C" int dcora_selfcheck_cholesky(int32_t k, const int32_t *rowptr, const 
   return DCORA_OK;
 }
 
+// Factor of Q + reg*I with `threads` host threads (subtree-parallel numeric phase): position
+// weighted checksum of L and nnz(L); the factor must not depend on the thread count.
+extern "C" int dcora_selfcheck_cholesky_threads(int32_t k, const int32_t *rowptr, const int32_t *col,
+                                                const double *val, int32_t dh, int32_t npose,
+                                                double reg, int32_t threads, double *checksum,
+                                                int64_t *factor_nnz) {
+  std::vector<int> Bp(k + 1, 0), Ai;
+  std::vector<double> Ax;
+  for (int i = 0; i < k; ++i) Bp[i + 1] = Bp[i] + (rowptr[i + 1] - rowptr[i]) + 1;
+  Ai.resize(Bp[k]); Ax.resize(Bp[k]);
+  for (int i = 0; i < k; ++i) {
+    int w = Bp[i];
+    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) { Ai[w] = col[p]; Ax[w] = val[p]; ++w; }
+    Ai[w] = i; Ax[w] = reg;
+  }
+  HostFactor F;
+  DCORA_TRY(sparse_cholesky(k, Bp, Ai, Ax, dh, npose, &F, DCORA_ORDERING_ND, TRSV_LEAF_ROWS, threads));
+  double cs = 0.0;
+  for (size_t i = 0; i < F.Lx.size(); ++i) cs += F.Lx[i] * std::cos(0.001 * (double)i) + 1e-3 * F.Li[i];
+  if (checksum) *checksum = cs;
+  if (factor_nnz) *factor_nnz = (int64_t)F.Lx.size();
+  return DCORA_OK;
+}
+
 #include "trsv.h"
 
 static int factor_for_check(int32_t k, const int32_t *rowptr, const int32_t *col,

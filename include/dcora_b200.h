@@ -356,6 +356,9 @@ void dcora_set_trsv_max_warps(int32_t warps);
 int dcora_selfcheck_layout(const dcora_agent_desc *agents, int32_t num_agents,
                            int32_t r, int32_t d, int32_t order,
                            double *max_abs_err);
+int dcora_selfcheck_cholesky_threads(int32_t k, const int32_t *rowptr, const int32_t *col,
+                                     const double *val, int32_t dh, int32_t npose, double reg,
+                                     int32_t threads, double *checksum, int64_t *factor_nnz);
 int dcora_selfcheck_coupling(const dcora_agent_desc *agents, int32_t num_agents,
                              int32_t r, int32_t d, int32_t order,
                              const dcora_halo_segment *segs, int32_t nseg,

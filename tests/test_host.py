@@ -217,3 +217,25 @@ def test_coupling_layout_is_exact_and_key_ordered(lib, S, robots, world):
         assert rc == 0, lib.dcora_last_error()
         assert err.value <= 1e-9 * max(1.0, np.abs(v).max() if len(v) else 1.0)
         assert bad.value == 0
+
+
+def test_subtree_parallel_cholesky_is_bit_identical(lib):
+    """The numeric phase factors independent elimination-tree subtrees on several host threads
+    (few large agents leave cores idle): same factor, bit for bit, whatever the thread count."""
+    from dcora_b200 import graph as pg, synthetic
+    import scipy.sparse as sp
+    meas, gt, idx = synthetic.grid3d(14, 0.1, seed=2)
+    gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, 2))
+    diag, _ = gp.split(agents=[0])
+    rp, ci, v = diag[0]
+    k = len(rp) - 1
+    assert k >= 4000          # below that the serial path is taken
+    out = []
+    for threads in (1, 2, 5):
+        cs, nnz = C.c_double(), C.c_int64()
+        rc = lib.dcora_selfcheck_cholesky_threads(
+            k, rp.ctypes.data_as(_lib.c_int32_p), ci.ctypes.data_as(_lib.c_int32_p),
+            v.ctypes.data_as(_lib.c_double_p), 1, 0, 0.05, threads, C.byref(cs), C.byref(nnz))
+        assert rc == 0
+        out.append((cs.value, nnz.value))
+    assert out[0] == out[1] == out[2], out
