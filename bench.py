@@ -303,8 +303,10 @@ def run_ours(args):
         cpu = cpu_baseline(args, gp, Xs if Xs is not None else X0, log)
 
     # ---- time-to-certified-solution (BASELINE.json metric, second half): the multi-agent
-    # staircase (RBCD -> distributed certificate -> escape -> next rank) on a partitioned
-    # range-aided grid, wall clock including assembly, factorisation and upload; the agents
+    # staircase (RBCD++ -> distributed certificate -> escape -> next rank; acceleration on like
+    # the reference drivers, MultiRobotExample.cpp:121, with the number of colours as the block
+    # count of the Nesterov sequences because a whole colour class moves per iteration) on a
+    # partitioned range-aided grid, wall clock including assembly, factorisation and upload; the agents
     # are dealt to all ranks of the job (collective)
     ttc = None
     if args.ttc_grid > 0:
@@ -313,9 +315,10 @@ def run_ours(args):
             import ttc_multi
             barrier()
             ttc = ttc_multi.run(args.ttc_grid, args.ttc_agents, args.rank, args.range_fraction,
-                                args.seed, acc=False, gradnorm_tol=0.1, eta=1e-3,
+                                args.seed, acc=True, gradnorm_tol=0.1, eta=1e-3,
                                 max_iters=args.ttc_max_iters, check_every=10,
-                                log=None, dist_rank=rank, world=world, device=local_rank)
+                                log=None, dist_rank=rank, world=world, device=local_rank,
+                                nesterov_blocks="colours", restart_interval=100)
             barrier()
             ttc["levels"] = [{k: v for k, v in lv.items() if k in
                               ("r", "sweeps", "gradnorm", "lambda_min", "residual", "is_psd", "converged", "solve_s", "certify_s")}

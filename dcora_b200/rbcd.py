@@ -167,7 +167,7 @@ class RBCD:
     def __init__(self, gp: GlobalProblem, r: int, rank=0, world=1, device=0,
                  params: ROptParameters | None = None, precond=True, group=None,
                  plan: RankPlan | None = None, diag=None, acceleration=False,
-                 restart_interval=30, _problem=None, k5_warps=None):
+                 restart_interval=30, _problem=None, k5_warps=None, nesterov_blocks=None):
         import torch
         self.torch = torch
         self.gp, self.r, self.rank, self.world, self.group = gp, r, rank, world, group
@@ -239,6 +239,11 @@ class RBCD:
         # RBCD++ (Nesterov acceleration, Agent.cpp:535-596,1158-1214; AgentParameters
         # acceleration / restartInterval, Agent.h:40-185)
         self.acc = bool(acceleration)
+        # N of updateGamma / updateAlpha (Agent.cpp:1189-1200): the number of blocks one of which
+        # is updated per iteration -- the number of agents in the reference; with the parallel
+        # colour schedule a whole colour class moves per iteration, so the number of COLOURS
+        # plays that role (nesterov_blocks='colours')
+        self.nesterov_blocks = nesterov_blocks
         self.restart_interval = int(restart_interval)
         self.it = 0
         if self.acc:
@@ -253,7 +258,8 @@ class RBCD:
         P.KH = self.P.KH
         return RBCD(self.gp, r, self.rank, self.world, self.device.index, self.params,
                     self.precond, self.group, plan=self.plan, acceleration=self.acc,
-                    restart_interval=self.restart_interval, _problem=P)
+                    restart_interval=self.restart_interval, _problem=P,
+                    nesterov_blocks=self.nesterov_blocks)
 
     # -- state ---------------------------------------------------------------
     def set_X(self, X_global):
@@ -338,6 +344,10 @@ class RBCD:
         agent's first solve (from Y) is overwritten by restartNesterovAcceleration's solve
         from XPrev, so only that one is run here."""
         N = self.gp.A
+        if self.nesterov_blocks == "colours":
+            N = max(1, self.plan.num_colors)
+        elif self.nesterov_blocks:
+            N = int(self.nesterov_blocks)
         self.it += 1
         Xprev = self.X
         self.gamma = (1 + np.sqrt(1 + 4 * N ** 2 * self.gamma ** 2)) / (2 * N)   # updateGamma

@@ -11,7 +11,7 @@ import numpy as np
 
 def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol=0.1, eta=1e-3,
         max_iters=1000, check_every=5, log=print, dist_rank=0, world=1, group=None, device=0,
-        r_max=None):
+        r_max=None, nesterov_blocks=None, restart_interval=30):
     import dcora_b200 as dc
     from dcora_b200 import graph as pg, rbcd, synthetic
     from dcora_b200.staircase import rbcd_staircase
@@ -21,13 +21,15 @@ def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol
     X0 = synthetic.lifted_initial_guess(meas, idx, gp, grid, rank)
     t1 = time.perf_counter()
     S = rbcd.RBCD(gp, rank, rank=dist_rank, world=world, device=device, group=group,
-                  params=dc.ROptParameters(time_bound_s=0.0), acceleration=acc)
+                  params=dc.ROptParameters(time_bound_s=0.0), acceleration=acc,
+                  nesterov_blocks=nesterov_blocks, restart_interval=restart_interval)
     t2 = time.perf_counter()
     res = rbcd_staircase(S, X0, r_max=r_max or rank + 3, eta=eta, gradnorm_tol=gradnorm_tol,
                          max_iters=max_iters, check_every=check_every, log=log)
     t3 = time.perf_counter()
     return {"workload": f"synthetic {grid}^3-pose 3D grid, {int(range_fraction * 100)}% range edges, "
-                        f"{agents} agents on {world} GPU(s), RBCD{'++' if acc else ''}, r0={rank}, "
+                        f"{agents} agents on {world} GPU(s), RBCD{'++' if acc else ''}"
+                        f"{' (N = colours, restart every ' + str(restart_interval) + ' iterations)' if acc and nesterov_blocks else ''}, r0={rank}, "
                         f"gradnorm_tol={gradnorm_tol}, eta={eta}",
             "poses": int(meas.n), "K": int(gp.K), "agents": agents, "certified": res.certified,
             "rank": res.rank, "cost_2f": 2 * res.cost, "gradnorm": res.gradnorm,
@@ -44,6 +46,8 @@ if __name__ == "__main__":
     ap.add_argument("--max-iters", type=int, default=1000)
     ap.add_argument("--check-every", type=int, default=5)
     ap.add_argument("--no-acc", action="store_true")
+    ap.add_argument("--nesterov-blocks", default=None, help="'colours' or an integer (default: agents)")
+    ap.add_argument("--restart-interval", type=int, default=30)
     ap.add_argument("--range-fraction", type=float, default=0.1,
                     help="0: pose graph only (the synthetic stand-in of the absent g2o100k, configs[3])")
     a = ap.parse_args()
@@ -56,7 +60,8 @@ if __name__ == "__main__":
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     log = (lambda m: print("[ttc] " + m, file=sys.stderr, flush=True)) if rk == 0 else None
     out = run(a.grid, a.agents, a.rank, range_fraction=a.range_fraction, acc=not a.no_acc, gradnorm_tol=a.tol, max_iters=a.max_iters,
-              check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev)
+              check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev,
+              nesterov_blocks=a.nesterov_blocks, restart_interval=a.restart_interval)
     if rk == 0:
         print(json.dumps(out))
     if world > 1:
