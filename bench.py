@@ -318,7 +318,7 @@ def run_ours(args):
                                 args.seed, acc=True, gradnorm_tol=0.1, eta=1e-3,
                                 max_iters=args.ttc_max_iters, check_every=10,
                                 log=None, dist_rank=rank, world=world, device=local_rank,
-                                nesterov_blocks="colours", restart_interval=100)
+                                nesterov_blocks="colours", restart_interval="auto")
             barrier()
             ttc["levels"] = [{k: v for k, v in lv.items() if k in
                               ("r", "sweeps", "gradnorm", "lambda_min", "residual", "is_psd", "converged", "solve_s", "certify_s")}

@@ -244,6 +244,10 @@ class RBCD:
         # colour schedule a whole colour class moves per iteration, so the number of COLOURS
         # plays that role (nesterov_blocks='colours')
         self.nesterov_blocks = nesterov_blocks
+        if restart_interval == "auto":
+            # measured on the 47^3-pose grid: the best interval between Nesterov restarts is about
+            # 5.5 sqrt(A) SWEEPS (22 sweeps for 16 agents, 45 for 64; profiles/r02_ttc_rbcdpp.txt)
+            restart_interval = max(30, int(round(5.5 * np.sqrt(gp.A))) * max(1, self.plan.num_colors))
         self.restart_interval = int(restart_interval)
         self.it = 0
         if self.acc:

@@ -127,7 +127,7 @@ def escape_distributed(S_next, X_dev, v_dev, theta, gradient_tolerance,
 
 def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, max_iters=1000,
                    check_every=5, certify_tol=1e-8, escape_tol=1e-4, round_solution=False,
-                   log=None) -> StaircaseResult:
+                   log=None, certify_max_iters=400) -> StaircaseResult:
     """Distributed Riemannian staircase on an RBCD state `S` (dcora_b200.rbcd.RBCD of any world
     size; every rank calls this collectively).  The drivers' defaults: RGradNormTol 0.1,
     min_eig_num_tol 1e-3, <= 1000 iterations per level (MultiRobotExample.cpp:121-133).
@@ -158,7 +158,7 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
                 if gn < gradnorm_tol:
                     break
         t1 = time.perf_counter()
-        cert = certify_distributed(S, eta, tol=certify_tol)
+        cert = certify_distributed(S, eta, tol=certify_tol, max_iters=certify_max_iters)
         t2 = time.perf_counter()
         levels.append(dict(r=r, f=f, gradnorm=gn, sweeps=sweeps, is_psd=bool(cert.is_psd),
                            lambda_min=cert.lambda_min, theta=cert.theta, residual=cert.residual,

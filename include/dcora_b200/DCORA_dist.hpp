@@ -590,9 +590,10 @@ class DistributedAgentBatch {
  public:
   // comm may be nullptr when world == 1
   DistributedAgentBatch(PartitionedProblem &P, unsigned r, int rank, int world, int device,
-                        ncclComm_t comm, bool acceleration = false, unsigned restart_interval = 30)
+                        ncclComm_t comm, bool acceleration = false, unsigned restart_interval = 30,
+                        int nesterov_blocks = 0)
       : r_(r), d_(P.d()), A_global_(P.numAgents()), comm_(comm), acc_(acceleration),
-        restart_interval_(restart_interval) {
+        restart_interval_(restart_interval), nesterov_blocks_(nesterov_blocks) {
     DCORA_B200_CUDA(cudaSetDevice(device));
     plan_ = makePlan(P, world, rank);
     const int A = plan_.a1 - plan_.a0;
@@ -694,7 +695,11 @@ class DistributedAgentBatch {
       return;
     }
     // RBCD++ (Agent.cpp:535-596,1158-1214); see dcora_b200/rbcd.py:_accelerated_step
-    const double N = (double)A_global_;
+    // N of updateGamma / updateAlpha: the number of agents (reference, nesterov_blocks = 0), a
+    // given block count, or the number of colours (-1: a whole colour class moves per iteration)
+    const double N = nesterov_blocks_ > 0 ? (double)nesterov_blocks_
+                     : nesterov_blocks_ < 0 ? (double)std::max(1, plan_.num_colors)
+                                            : (double)A_global_;
     ++it_;
     gamma_ = (1 + std::sqrt(1 + 4 * N * N * gamma_ * gamma_)) / (2 * N);
     alpha_ = 1 / (gamma_ * N);
@@ -758,6 +763,7 @@ class DistributedAgentBatch {
   ncclComm_t comm_;
   bool acc_;
   unsigned restart_interval_;
+  int nesterov_blocks_;
   RankPlan plan_;
   std::shared_ptr<detail::Handle> h_;
   dcora_ropt_params params_;

@@ -35,7 +35,7 @@ class AgentBlock:
 
 class RBCD:
     def __init__(self, blocks, cross, params: solver.ROptParameters | None = None,
-                 acceleration=False, restart_interval=30):
+                 acceleration=False, restart_interval=30, nesterov_blocks=None):
         self.blocks = blocks
         self.C = sp.csr_matrix(cross)
         self.Ct = self.C.T.tocsr()        # row-slicing by output column
@@ -43,6 +43,9 @@ class RBCD:
         self.acc = acceleration
         self.restart_interval = restart_interval
         self.A = len(blocks)
+        # N of updateGamma / updateAlpha: number of agents (reference), or the number of
+        # blocks of the schedule when a whole colour class moves per iteration
+        self.N = int(nesterov_blocks) if nesterov_blocks else len(blocks)
         self.it = 0
         self.results = [None] * self.A
 
@@ -83,7 +86,7 @@ class RBCD:
         # public states (MultiRobotExample.cpp:228-258): the neighbour states that
         # enter G are the neighbours' new X, i.e. their Y -- or, on a restart
         # iteration (all agents share the counter), their XPrev (:1165-1176).
-        N = self.A
+        N = self.N
         Xprev = self.X.copy()
         self.gamma = (1 + np.sqrt(1 + 4 * N ** 2 * self.gamma ** 2)) / (2 * N)
         self.alpha = 1 / (self.gamma * N)

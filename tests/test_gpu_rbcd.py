@@ -171,18 +171,22 @@ def test_combine_project_is_the_nesterov_building_block(name, robots):
         assert rel_err(out[:, s], ref) < 1e-12
 
 
-def test_accelerated_sweeps_follow_the_oracle():
-    # RBCD++ with restart (Agent.cpp:535-596,1158-1214) on smallGrid3D / 5 robots
+@pytest.mark.parametrize("by_colours", [False, True], ids=["N=agents", "N=colours"])
+def test_accelerated_sweeps_follow_the_oracle(by_colours):
+    # RBCD++ with restart (Agent.cpp:535-596,1158-1214) on smallGrid3D / 5 robots; with the
+    # reference's N = number of agents, and with N = number of colours (the block count of the
+    # parallel colour schedule)
     import dcora_b200 as dc
     from dcora_b200 import rbcd
     r = 5
     gp, blocks, cross = _setup("smallGrid3D", 5, r)
     X0 = _random_X(blocks, r, gp.K, 6)
     G = rbcd.RBCD(gp, r, params=dc.ROptParameters(time_bound_s=0.0), acceleration=True,
-                  restart_interval=7)
+                  restart_interval=7, nesterov_blocks="colours" if by_colours else None)
     for a, b in enumerate(blocks):
         b.P.reg = G.P.precond_reg(a)
-    O = orbcd.RBCD(blocks, cross, solver.ROptParameters(), acceleration=True, restart_interval=7)
+    O = orbcd.RBCD(blocks, cross, solver.ROptParameters(), acceleration=True, restart_interval=7,
+                   nesterov_blocks=G.plan.num_colors if by_colours else None)
     G.set_X(X0)
     O.set_X(X0)
     colors = G.plan.colors

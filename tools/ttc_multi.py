@@ -11,7 +11,8 @@ import numpy as np
 
 def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol=0.1, eta=1e-3,
         max_iters=1000, check_every=5, log=print, dist_rank=0, world=1, group=None, device=0,
-        r_max=None, nesterov_blocks=None, restart_interval=30):
+        r_max=None, nesterov_blocks=None, restart_interval=30, certify_max_iters=400,
+        agent_tol=None):
     import dcora_b200 as dc
     from dcora_b200 import graph as pg, rbcd, synthetic
     from dcora_b200.staircase import rbcd_staircase
@@ -20,18 +21,25 @@ def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol
     gp = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, agents))
     X0 = synthetic.lifted_initial_guess(meas, idx, gp, grid, rank)
     t1 = time.perf_counter()
+    # every agent stops its own RTR at `agent_tol` (reference default 1e-2, QuadraticOptimizer):
+    # the global gradient norm cannot fall below ~sqrt(A) * agent_tol, so many agents need a
+    # proportionally smaller one to reach the drivers' RGradNormTol
+    if agent_tol is None:
+        agent_tol = min(1e-2, 0.5 * gradnorm_tol / np.sqrt(agents))
     S = rbcd.RBCD(gp, rank, rank=dist_rank, world=world, device=device, group=group,
-                  params=dc.ROptParameters(time_bound_s=0.0), acceleration=acc,
+                  params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=agent_tol), acceleration=acc,
                   nesterov_blocks=nesterov_blocks, restart_interval=restart_interval)
     t2 = time.perf_counter()
     res = rbcd_staircase(S, X0, r_max=r_max or rank + 3, eta=eta, gradnorm_tol=gradnorm_tol,
-                         max_iters=max_iters, check_every=check_every, log=log)
+                         max_iters=max_iters, check_every=check_every, log=log,
+                         certify_max_iters=certify_max_iters)
     t3 = time.perf_counter()
     return {"workload": f"synthetic {grid}^3-pose 3D grid, {int(range_fraction * 100)}% range edges, "
                         f"{agents} agents on {world} GPU(s), RBCD{'++' if acc else ''}"
                         f"{' (N = colours, restart every ' + str(restart_interval) + ' iterations)' if acc and nesterov_blocks else ''}, r0={rank}, "
                         f"gradnorm_tol={gradnorm_tol}, eta={eta}",
-            "poses": int(meas.n), "K": int(gp.K), "agents": agents, "certified": res.certified,
+            "poses": int(meas.n), "K": int(gp.K), "agents": agents, "agent_gradnorm_tol": agent_tol,
+            "certified": res.certified,
             "rank": res.rank, "cost_2f": 2 * res.cost, "gradnorm": res.gradnorm,
             "lambda_min": res.lambda_min, "assemble_s": t1 - t0, "factor_upload_s": t2 - t1,
             "solve_certify_s": t3 - t2, "seconds": t3 - t0, "levels": res.levels}
@@ -47,7 +55,8 @@ if __name__ == "__main__":
     ap.add_argument("--check-every", type=int, default=5)
     ap.add_argument("--no-acc", action="store_true")
     ap.add_argument("--nesterov-blocks", default=None, help="'colours' or an integer (default: agents)")
-    ap.add_argument("--restart-interval", type=int, default=30)
+    ap.add_argument("--restart-interval", default="30", help="iterations (colour steps) or 'auto'")
+    ap.add_argument("--certify-max-iters", type=int, default=400)
     ap.add_argument("--range-fraction", type=float, default=0.1,
                     help="0: pose graph only (the synthetic stand-in of the absent g2o100k, configs[3])")
     a = ap.parse_args()
@@ -61,7 +70,9 @@ if __name__ == "__main__":
     log = (lambda m: print("[ttc] " + m, file=sys.stderr, flush=True)) if rk == 0 else None
     out = run(a.grid, a.agents, a.rank, range_fraction=a.range_fraction, acc=not a.no_acc, gradnorm_tol=a.tol, max_iters=a.max_iters,
               check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev,
-              nesterov_blocks=a.nesterov_blocks, restart_interval=a.restart_interval)
+              nesterov_blocks=a.nesterov_blocks,
+              restart_interval=a.restart_interval if a.restart_interval == "auto" else int(a.restart_interval),
+              certify_max_iters=a.certify_max_iters)
     if rk == 0:
         print(json.dumps(out))
     if world > 1:
