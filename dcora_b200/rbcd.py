@@ -239,6 +239,7 @@ class RBCD:
         # RBCD++ (Nesterov acceleration, Agent.cpp:535-596,1158-1214; AgentParameters
         # acceleration / restartInterval, Agent.h:40-185)
         self.acc = bool(acceleration)
+        self.acc0 = self.acc          # disable_acceleration() is per staircase level
         # N of updateGamma / updateAlpha (Agent.cpp:1189-1200): the number of blocks one of which
         # is updated per iteration -- the number of agents in the reference; with the parallel
         # colour schedule a whole colour class moves per iteration, so the number of COLOURS
@@ -261,7 +262,7 @@ class RBCD:
         P = self.P.with_rank(r)
         P.KH = self.P.KH
         return RBCD(self.gp, r, self.rank, self.world, self.device.index, self.params,
-                    self.precond, self.group, plan=self.plan, acceleration=self.acc,
+                    self.precond, self.group, plan=self.plan, acceleration=self.acc0,
                     restart_interval=self.restart_interval, _problem=P,
                     nesterov_blocks=self.nesterov_blocks)
 
@@ -283,6 +284,14 @@ class RBCD:
             self.alpha = 0.0
         else:
             self.P.set_iterate_tracking(True)   # forget the tracked copy
+
+    def disable_acceleration(self):
+        """Continue with plain RBCD from the current iterate (used when the accelerated
+        sequence stalls: RBCD++ is not monotone, RBCD is)."""
+        if self.acc:
+            self.acc = False
+            self.V = self.Y = None
+            self.P.set_iterate_tracking(True)
 
     def _count(self, active):
         """Bookkeeping of an optimize() call over the agents in `active`."""
