@@ -5,7 +5,9 @@
 // the NCCL id and hands it to the others through shared memory.
 //
 //   rbcd_ra <file.pyfg> [--ranks N] [--rank R] [--iters I] [--tol T] [--acc]
-//           [--x0 x0.bin] [--out x.bin]
+//           [--nesterov-blocks B] [--restart I] [--x0 x0.bin] [--out x.bin]
+// --nesterov-blocks -1: the number of colours as block count of RBCD++ (a colour class moves per
+// iteration); 0 (default): the number of agents as in the reference.
 // x0.bin / x.bin: r x K doubles, column-major, agent-major reference ordering (default start:
 // the file's ground truth lifted with [I; 0]).  Prints one JSON line per iteration (rank 0).
 #include <sys/mman.h>
@@ -33,6 +35,8 @@ int main(int argc, char **argv) {
   unsigned r = 5, iters = 10;
   double tol = 0.1;   // RGradNormTol (MultiRobotExample_RASLAM.cpp:101)
   bool acc = false;
+  int nesterov_blocks = 0;          // 0: agents (reference), -1: colours, > 0: given
+  unsigned restart_interval = 30;   // AgentParameters::restartInterval
   std::string x0_file, out_file;
   for (int i = 2; i < argc; ++i) {
     auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
@@ -41,6 +45,8 @@ int main(int argc, char **argv) {
     else if (!std::strcmp(argv[i], "--iters")) iters = std::atoi(next());
     else if (!std::strcmp(argv[i], "--tol")) tol = std::atof(next());
     else if (!std::strcmp(argv[i], "--acc")) acc = true;
+    else if (!std::strcmp(argv[i], "--nesterov-blocks")) nesterov_blocks = std::atoi(next());
+    else if (!std::strcmp(argv[i], "--restart")) restart_interval = std::atoi(next());
     else if (!std::strcmp(argv[i], "--x0")) x0_file = next();
     else if (!std::strcmp(argv[i], "--out")) out_file = next();
   }
@@ -106,7 +112,8 @@ int main(int argc, char **argv) {
   int rc = 0;
   {
     const auto t0 = std::chrono::steady_clock::now();
-    DCORA::DistributedAgentBatch agents(problem, r, rank, world, rank, comm, acc);
+    DCORA::DistributedAgentBatch agents(problem, r, rank, world, rank, comm, acc, restart_interval,
+                                        nesterov_blocks);
     agents.setX(X0);
     const double setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     double cost = 0.0, gradnorm = 0.0;
