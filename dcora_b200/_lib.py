@@ -106,6 +106,8 @@ SYMBOLS = {
     "dcora_project_to_rotation_group": (C.c_int, [c_double_p, C.c_int32, c_double_p]),
     "dcora_problem_round_solution": (C.c_int, [VP, VP, VP]),
     "dcora_problem_align_trajectory": (C.c_int, [VP, VP, c_double_p, C.c_int32, VP]),
+    "dcora_problem_certificate_prepare": (C.c_int, [VP, VP, VP]),
+    "dcora_problem_certificate_apply": (C.c_int, [VP, VP, VP, VP]),
     "dcora_problem_cost_terms": (C.c_int, [VP, VP, c_double_p, c_double_p]),
     "dcora_problem_combine_project": (C.c_int, [VP, C.c_double, VP, C.c_double, VP,
                                                 c_uint8_p, VP]),

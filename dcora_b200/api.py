@@ -409,6 +409,20 @@ class QuadraticProblem:
             self.h, a.ptr, T.ctypes.data_as(C.POINTER(C.c_double)), int(bool(is_global)), o.ptr))
         return out
 
+    def certificate_prepare(self, X, XQ):
+        """Lambda(X) of the handle's agents from X and (X Q_global) on its columns."""
+        a, b = _Arg(X, self.r, self.K), _Arg(XQ, self.r, self.K)
+        check(self.lib.dcora_problem_certificate_prepare(self.h, a.ptr, b.ptr))
+
+    def certificate_apply(self, V, QV, out=None):
+        """S V = QV - V Lambda for a block of r vectors (after certificate_prepare)."""
+        a, b = _Arg(V, self.r, self.K), _Arg(QV, self.r, self.K)
+        if out is None:
+            out = _new_out(V, self.r, self.K)
+        o = _Arg(out, self.r, self.K, out=True)
+        check(self.lib.dcora_problem_certificate_apply(self.h, a.ptr, b.ptr, o.ptr))
+        return out
+
     def cost_terms(self, X):
         a = _Arg(X, self.r, self.K)
         q = (C.c_double * self.A)()

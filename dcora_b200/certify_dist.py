@@ -11,16 +11,16 @@ vectors at once (the C-ABI works on K x r matrices; the r rows of V^T are indepe
 vectors for a right-multiplication by the symmetric Q):
     (V Q_global)_local = V Q_diag + [V | halo(V)] C      update_G(V, halo) ; egrad(V)
     (V Lambda)_local   : Lambda = sym-block-diag(X^T (X Q_global)) on the rotation
-                         blocks, <r_k, (X Q)_k> on the unit spheres -- d x d blocks, applied
-                         here with torch on the device.
+                         blocks, <r_k, (X Q)_k> on the unit spheres -- built and applied by the
+                         library (dcora_problem_certificate_prepare / _apply, csrc/certify.cu).
 lambda_min is computed like dcora_certify does on one handle (csrc/certify.cu): a Krylov-type
 iteration from a RANDOM start (here block Davidson / Rayleigh-Ritz with block size r and thick
 restart, residuals preconditioned by the agents' own Cholesky factors = block Jacobi) until its smallest Ritz pair has converged, then a Rayleigh-Ritz step on span(rows of
 X) -- at a critical point they span the null space of S, the cluster a random start resolves
 last -- and the smaller of the two upper bounds is reported.  (The rows of X must NOT seed the
 iteration: they are exact eigenvectors, their Ritz pair "converges" at once and would hide a
-negative eigenvalue at a saddle.)  Host side only: torch for the small dense algebra and NCCL,
-no kernels of its own.
+negative eigenvalue at a saddle.)  torch is used for the tall-skinny dense algebra of the iteration (Gram
+matrices, basis rotations: library GEMMs) and NCCL; S V itself runs in the library's kernels.
 """
 from __future__ import annotations
 
@@ -39,19 +39,6 @@ class DistCertificate:
     converged: bool
     theta: float = 0.0     # v^T S v of the returned direction (fastVerification's theta)
     v: object = None       # local rows of the unit eigenvector estimate (device tensor, K_local)
-
-
-def _local_indices(S):
-    """Local reference columns of the rotation blocks (n, d) and unit spheres (l,)."""
-    gp, p = S.gp, S.plan
-    poses = np.nonzero((gp.robot_of_pose >= p.a0) & (gp.robot_of_pose < p.a1))[0]
-    rot = gp.rot_cols(poses) - p.c0 if len(poses) else np.zeros((0, gp.d), np.int64)
-    if gp.ra and len(gp.sph_robot):
-        sph = np.nonzero((gp.sph_robot >= p.a0) & (gp.sph_robot < p.a1))[0]
-        sph = gp.sphere_col(sph) - p.c0
-    else:
-        sph = np.zeros(0, np.int64)
-    return rot, sph
 
 
 def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
@@ -91,31 +78,18 @@ def certify_distributed(S, eta, tol=1e-9, max_iters=400, max_basis=None, seed=0,
             P.update_G(V, halo_of(V), None)
             return P.EucGrad(V)
 
-        # Lambda from the iterate (constructDualCertificateMatrix*, :1898-1982)
+        # Lambda from the iterate (constructDualCertificateMatrix*, :1898-1982): kept on the
+        # handle by dcora_problem_certificate_prepare, applied by ..._certificate_apply
         X = S.X
         XQ = times_Q(X)
-        rot_np, sph_np = _local_indices(S)
-        rot = t.from_numpy(rot_np.reshape(-1)).to(dev)
-        n_loc, d = rot_np.shape
-        sph = t.from_numpy(sph_np).to(dev)
-        Yb = X.index_select(0, rot).reshape(n_loc, d, r)
-        Eb = XQ.index_select(0, rot).reshape(n_loc, d, r)
-        Lam = Yb @ Eb.transpose(1, 2)
-        Lam = 0.5 * (Lam + Lam.transpose(1, 2))                     # (n, d, d)
-        lam_s = (X.index_select(0, sph) * XQ.index_select(0, sph)).sum(1) if len(sph_np) else None
+        P.certificate_prepare(X, XQ)
 
         nprod = 0
 
         def times_S(V):
             nonlocal nprod
             nprod += 1
-            W = times_Q(V)
-            if n_loc:
-                Vb = V.index_select(0, rot).reshape(n_loc, d, r)
-                W.index_add_(0, rot, -(Lam @ Vb).reshape(n_loc * d, r))
-            if lam_s is not None:
-                W.index_add_(0, sph, -(lam_s[:, None] * V.index_select(0, sph)))
-            return W
+            return P.certificate_apply(V, times_Q(V))
 
         def gram(A, B):
             return allsum(A.T @ B)

@@ -49,6 +49,41 @@ lambda_apply_kernel(const Chunk *__restrict__ chunks, int R,
   }
 }
 
+// The same for a block of R vectors at once (the rows of V^T, K x R column-major R x K like
+// every iterate): OUT = QV - V * Lambda.  The distributed certificate applies S to R vectors
+// per product (dcora_problem_certificate_apply).
+template <int DH>
+__global__ void __launch_bounds__(128)
+lambda_apply_block_kernel(const Chunk *__restrict__ chunks, int R,
+                          const double *__restrict__ Lam, const double *__restrict__ V,
+                          const double *__restrict__ QV, double *__restrict__ OUT) {
+  constexpr int D = DH - 1;
+  const Chunk ch = chunks[blockIdx.x];
+  const int n = ch.ncols * R;
+  if (ch.kind == KIND_POSE) {
+    for (int t = threadIdx.x; t < n; t += 128) {
+      const int c = t / R, q = t - c * R;
+      const int pi = c / DH, a = c - pi * DH;
+      const size_t o = (size_t)(ch.col0 + c) * R + q;
+      double s = QV[o];
+      if (a < D) {
+        const size_t pb = (size_t)(ch.col0 + pi * DH) * R;
+#pragma unroll
+        for (int b = 0; b < D; ++b) s -= Lam[pb + a * D + b] * V[pb + (size_t)b * R + q];
+      }
+      OUT[o] = s;
+    }
+  } else if (ch.kind == KIND_SPHERE) {
+    for (int t = threadIdx.x; t < n; t += 128) {
+      const int c = t / R;
+      const size_t o = (size_t)ch.col0 * R + t;
+      OUT[o] = QV[o] - Lam[(size_t)(ch.col0 + c) * R] * V[o];
+    }
+  } else {
+    for (int t = threadIdx.x; t < n; t += 128) OUT[(size_t)ch.col0 * R + t] = QV[(size_t)ch.col0 * R + t];
+  }
+}
+
 constexpr int LZ_BLOCK = 256;
 constexpr int LZ_ROWS = 2048;   // rows per CTA in the tall-skinny kernels
 constexpr int LZ_MAXM = 64;
@@ -654,6 +689,40 @@ extern "C" int dcora_certify(dcora_problem *p, const double *X, double eta,
   cleanup();
 #undef CERT_CUDA
   return DCORA_OK;
+}
+
+// Distributed certificate (dcora_b200/certify_dist.py): the multipliers of the batch from the
+// iterate and X * Q_global, kept on the handle ...
+extern "C" int dcora_problem_certificate_prepare(dcora_problem *p, const double *X,
+                                                 const double *XQ) {
+  if (!p || !X || !XQ) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  double *x = p->vec(WS_IO0), *xq = p->vec(WS_IO1), *Lam = p->vec(WS_S);
+  if (!x || !xq || !Lam) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, X, x, p->r));
+  DCORA_TRY(import_matrix(p, XQ, xq, p->r));
+  DCORA_TRY(launch_sym_ytg(p, x, xq, Lam, -1));
+  DCORA_CUDA(cudaStreamSynchronize(p->stream));
+  return DCORA_OK;
+}
+
+// ... and OUT = QV - V * Lambda for a block of r vectors (S V restricted to this handle's
+// columns, QV = V * Q_global from dcora_problem_update_G + dcora_problem_egrad)
+extern "C" int dcora_problem_certificate_apply(dcora_problem *p, const double *V,
+                                               const double *QV, double *OUT) {
+  if (!p || !V || !QV || !OUT) return DCORA_ERR_ARG;
+  DCORA_CUDA(cudaSetDevice(p->M->device));
+  DeviceMatrices &M = *p->M;
+  double *v = p->vec(WS_IO0), *qv = p->vec(WS_IO1), *o = p->vec(WS_IO2), *Lam = p->vec(WS_S);
+  if (!v || !qv || !o || !Lam) return DCORA_ERR_ALLOC;
+  DCORA_TRY(import_matrix(p, V, v, p->r));
+  DCORA_TRY(import_matrix(p, QV, qv, p->r));
+  if (M.d == 3)
+    lambda_apply_block_kernel<4><<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->r, Lam, v, qv, o);
+  else
+    lambda_apply_block_kernel<3><<<M.nchunks, 128, 0, p->stream>>>(M.chunks, p->r, Lam, v, qv, o);
+  DCORA_LAUNCH_CHECK(p);
+  return export_matrix(p, o, OUT, p->r);
 }
 
 extern "C" int dcora_problem_escape_saddle(dcora_problem *p, const double *Xopt,

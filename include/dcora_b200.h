@@ -296,6 +296,18 @@ int dcora_problem_round_solution(dcora_problem *p, const double *X, double *Xd);
 int dcora_problem_align_trajectory(dcora_problem *p, const double *X, const double *Tw0,
                                    int32_t is_global, double *Td);
 
+/* Certificate of the PARTITIONED problem (constructDualCertificateMatrix{PGO,RASLAM},
+ * src/DCORA_utils.cpp:1898-1982, applied implicitly and blockwise).
+ * dcora_problem_certificate_prepare: Lambda of this handle's agents from the iterate X and
+ * XQ = (X * Q_global) restricted to the handle's columns (dcora_problem_update_G with the halo
+ * + dcora_problem_egrad give it): sym(Y_i^T (XQ)_i) per rotation block, <r_k, (XQ)_k> per unit
+ * sphere; kept on the handle until the next prepare / certify / RTR call.
+ * dcora_problem_certificate_apply: OUT = QV - V * Lambda for a block of r vectors (r x K like an
+ * iterate), i.e. S V on the handle's columns given QV = V * Q_global. */
+int dcora_problem_certificate_prepare(dcora_problem *p, const double *X, const double *XQ);
+int dcora_problem_certificate_apply(dcora_problem *p, const double *V, const double *QV,
+                                    double *OUT);
+
 /* Per-agent 0.5 <X Q, X> and <X, G>: the global cost of the partitioned
  * problem is sum_a quad_a + 0.5 lin_a (cross terms appear in two agents). */
 int dcora_problem_cost_terms(dcora_problem *p, const double *X, double *quad_out,
