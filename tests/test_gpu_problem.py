@@ -87,3 +87,39 @@ def test_device_resident_arguments(pair):
     out = gp.EucGrad(Xd)
     assert out.is_cuda
     assert rel_err(out.cpu().numpy().T, P.egrad(X)) < 1e-13
+
+
+@pytest.fixture(scope="module")
+def big_agent():
+    from dcora_b200 import graph as pg, synthetic
+    from oracle import solver
+    meas, gt, idx = synthetic.grid3d(15, 0.1, seed=8)
+    gpm = pg.GlobalProblem(meas, pg.Partition.contiguous(meas.n, 1))
+    Q = gpm.Q()
+    L = mf.Layout(4, 3, int(gpm.n_a[0]), int(gpm.l_a[0]), 0, ra=True)
+    assert L.k >= 12000
+    P = solver.QuadraticProblem(L, Q, precond_reg=0.5)
+    rng = np.random.default_rng(3)
+    X = mf.random_point(L, rng)
+    V = rng.standard_normal((4, L.k))
+    ref_solve = P._factor().solve(np.ascontiguousarray(V.T)).T
+    return L, Q, X, V, ref_solve, P.precondition(X, V)
+
+
+@pytest.mark.parametrize("warps", [64, 96, 128, 256])
+def test_precondition_cluster_shapes(big_agent, warps):
+    # K5 on a LARGE agent (>= 12000 columns) with every cluster shape the drivers choose from:
+    # 64 warps (8 CTAs x 8), 96 (12 x 8), 128 (16 x 8), 256 (16 x 16) per agent
+    # (dcora_set_trsv_max_warps); all must solve (Q + reg I) z = v like the oracle's LU
+    import dcora_b200 as dc
+    from dcora_b200 import _lib
+    L, Q, X, V, ref_solve, ref_precond = big_agent
+    lib = _lib.load()
+    lib.dcora_set_trsv_max_warps(warps)
+    try:
+        ag = dc.AgentData(n=L.n, l=L.l, b=0, Q=Q, precond_reg=0.5)
+        gp = dc.QuadraticProblem(ag, 4, 3, dc.ORDER_RA)
+    finally:
+        lib.dcora_set_trsv_max_warps(64)
+    assert rel_err(gp.factor_solve(V), ref_solve) < 1e-9
+    assert rel_err(gp.PreCondition(X, V), ref_precond) < 1e-9
