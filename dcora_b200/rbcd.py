@@ -285,6 +285,15 @@ class RBCD:
         else:
             self.P.set_iterate_tracking(True)   # forget the tracked copy
 
+    def restart_acceleration(self):
+        """restartNesterovAcceleration (Agent.cpp:1165-1176) on demand: V = Y = X, gamma = 0
+        (the momentum is dropped, the iterate kept)."""
+        if self.acc:
+            self.V = self.X.clone()
+            self.Y = self.X.clone()
+            self.gamma = 0.0
+            self.alpha = 0.0
+
     def disable_acceleration(self):
         """Continue with plain RBCD from the current iterate (used when the accelerated
         sequence stalls: RBCD++ is not monotone, RBCD is)."""

@@ -127,7 +127,8 @@ def escape_distributed(S_next, X_dev, v_dev, theta, gradient_tolerance,
 
 def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, max_iters=1000,
                    check_every=5, certify_tol=1e-8, escape_tol=1e-4, round_solution=False,
-                   log=None, certify_max_iters=400, stall_checks=0) -> StaircaseResult:
+                   log=None, certify_max_iters=400, stall_checks=0,
+                   adaptive_restart=False) -> StaircaseResult:
     """Distributed Riemannian staircase on an RBCD state `S` (dcora_b200.rbcd.RBCD of any world
     size; every rank calls this collectively).  The drivers' defaults: RGradNormTol 0.1,
     min_eig_num_tol 1e-3, <= 1000 iterations per level (MultiRobotExample.cpp:121-133).
@@ -135,6 +136,8 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
     Per level: parallel-coloured RBCD / RBCD++ sweeps until the global gradient norm is below
     `gradnorm_tol` -> certify_distributed -> (not PSD) escape_distributed to rank r + 1 on a
     handle that shares Q, the Cholesky factors and the coupling with the previous level.
+    `adaptive_restart`: drop the Nesterov momentum whenever the monitored gradient norm went up
+    between two checks (gradient-based adaptive restart) on top of the fixed restart interval.
     `stall_checks` > 0: when an accelerated level has not improved its best gradient norm by
     20 % over that many consecutive checks, it continues with plain (monotone) RBCD sweeps.
     Returns a StaircaseResult whose X is the LOCAL (r, K_local) iterate of this rank."""
@@ -150,6 +153,7 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
         f = gn = None
         sweeps = 0
         best, since_best, switched_at = float("inf"), 0, None
+        prev_gn, n_adaptive = None, 0
         for it in range(int(max_iters)):
             S.iterate()
             sweeps += 1
@@ -160,6 +164,10 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
                         f"({time.perf_counter() - t_start:.1f} s)")
                 if gn < gradnorm_tol:
                     break
+                if adaptive_restart and S.acc and prev_gn is not None and gn > prev_gn:
+                    S.restart_acceleration()
+                    n_adaptive += 1
+                prev_gn = gn
                 if gn < 0.8 * best:
                     best, since_best = gn, 0
                 else:
@@ -174,6 +182,7 @@ def rbcd_staircase(S, X0_global=None, r_max=None, eta=1e-3, gradnorm_tol=0.1, ma
         cert = certify_distributed(S, eta, tol=certify_tol, max_iters=certify_max_iters)
         t2 = time.perf_counter()
         levels.append(dict(r=r, f=f, gradnorm=gn, sweeps=sweeps, plain_rbcd_from=switched_at,
+                           adaptive_restarts=n_adaptive,
                            is_psd=bool(cert.is_psd),
                            lambda_min=cert.lambda_min, theta=cert.theta, residual=cert.residual,
                            products=cert.products, converged=bool(cert.converged),

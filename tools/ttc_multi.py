@@ -12,7 +12,7 @@ import numpy as np
 def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol=0.1, eta=1e-3,
         max_iters=1000, check_every=5, log=print, dist_rank=0, world=1, group=None, device=0,
         r_max=None, nesterov_blocks=None, restart_interval=30, certify_max_iters=400,
-        agent_tol=None, stall_checks=0):
+        agent_tol=None, stall_checks=0, adaptive_restart=False):
     import dcora_b200 as dc
     from dcora_b200 import graph as pg, rbcd, synthetic
     from dcora_b200.staircase import rbcd_staircase
@@ -32,7 +32,8 @@ def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol
     t2 = time.perf_counter()
     res = rbcd_staircase(S, X0, r_max=r_max or rank + 3, eta=eta, gradnorm_tol=gradnorm_tol,
                          max_iters=max_iters, check_every=check_every, log=log,
-                         certify_max_iters=certify_max_iters, stall_checks=stall_checks)
+                         certify_max_iters=certify_max_iters, stall_checks=stall_checks,
+                         adaptive_restart=adaptive_restart)
     t3 = time.perf_counter()
     return {"workload": f"synthetic {grid}^3-pose 3D grid, {int(range_fraction * 100)}% range edges, "
                         f"{agents} agents on {world} GPU(s), RBCD{'++' if acc else ''}"
@@ -58,6 +59,7 @@ if __name__ == "__main__":
     ap.add_argument("--restart-interval", default="30", help="iterations (colour steps) or 'auto'")
     ap.add_argument("--certify-max-iters", type=int, default=400)
     ap.add_argument("--stall-checks", type=int, default=0)
+    ap.add_argument("--adaptive-restart", action="store_true")
     ap.add_argument("--range-fraction", type=float, default=0.1,
                     help="0: pose graph only (the synthetic stand-in of the absent g2o100k, configs[3])")
     a = ap.parse_args()
@@ -73,7 +75,8 @@ if __name__ == "__main__":
               check_every=a.check_every, log=log, dist_rank=rk, world=world, device=dev,
               nesterov_blocks=a.nesterov_blocks,
               restart_interval=a.restart_interval if a.restart_interval == "auto" else int(a.restart_interval),
-              certify_max_iters=a.certify_max_iters, stall_checks=a.stall_checks)
+              certify_max_iters=a.certify_max_iters, stall_checks=a.stall_checks,
+              adaptive_restart=a.adaptive_restart)
     if rk == 0:
         print(json.dumps(out))
     if world > 1:
