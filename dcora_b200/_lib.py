@@ -24,7 +24,7 @@ class ROptParams(C.Structure):
                 ("RGD_use_preconditioner", C.c_int32), ("RTR_iterations", C.c_int32),
                 ("RTR_tCG_iterations", C.c_int32), ("RTR_initial_radius", C.c_double),
                 ("time_bound_s", C.c_double), ("retraction", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("stable_decrease", C.c_int32)]
 
 
 class ROptResult(C.Structure):

@@ -53,6 +53,8 @@ class ROptParameters:
     RTR_initial_radius: float = 100.0
     time_bound_s: float = 5.0      # QuadraticOptimizer.cpp:252; <=0 disables
     retraction: int = RETRACT_QF
+    # rho of RTR from <egrad, d> + 0.5 <dQ, d> instead of f(x) - f(x+): see dcora_ropt_params
+    stable_decrease: bool = False
 
     def to_c(self):
         p = ROptParams()
@@ -66,6 +68,7 @@ class ROptParameters:
         p.RTR_initial_radius = self.RTR_initial_radius
         p.time_bound_s = self.time_bound_s
         p.retraction = self.retraction
+        p.stable_decrease = int(self.stable_decrease)
         return p
 
 

@@ -18,7 +18,7 @@ int launch_cluster_r8(dcora_problem *, const ClusterArgs &, int, int);
 // The one-launch solve is used for agents that fit one CTA (< 1500 columns: 8 or 16 warps).
 bool rtr_cluster_applicable(const dcora_problem *p, const dcora_ropt_params *prm) {
   static const char *force = getenv("DCORA_RTR_PATH");   // "host": never
-  if (prm->method != 0) return false;
+  if (prm->method != 0 || prm->stable_decrease) return false;
   if (p->r < p->M->d || p->r < CLUSTER_MIN_RANK || p->r > CLUSTER_MAX_RANK) return false;
   if (force && force[0] == 'h') return false;
   const DeviceMatrices &M = *p->M;

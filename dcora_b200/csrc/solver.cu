@@ -186,16 +186,26 @@ tcg_stepC_kernel(const int *list, const int *agent_chunk0, const double *partial
 // S_F2 holds f(x2); partial 0 = <eta, gf1>, partial 1 = <eta, H eta>
 __global__ void __launch_bounds__(128)
 rtr_rho_kernel(const int *list, const int *agent_chunk0, const double *partials, int *flags,
-               double *scal, int single_mode) {
+               double *scal, int single_mode, int stable) {
   __shared__ double sm[4];
   const int a = list ? list[blockIdx.x] : blockIdx.x;
   int *f = flags + a * NF;
   if (f[F_OUTER] == 0) { if (threadIdx.x == 0) f[F_ACCEPT] = 0; return; }
-  const double eg = agent_sum(agent_chunk0, partials, a, 0, sm);
-  const double eh = agent_sum(agent_chunk0, partials, a, 1, sm);
+  // stable: slots 0, 1 = <d, EG>, <d, dQ> (d = x2 - x1), slots 2, 3 = <eta, gf>, <eta, H eta>
+  const double eg = agent_sum(agent_chunk0, partials, a, stable ? 2 : 0, sm);
+  const double eh = agent_sum(agent_chunk0, partials, a, stable ? 3 : 1, sm);
+  double dEG = 0.0, dQd = 0.0;
+  if (stable) {
+    dEG = agent_sum(agent_chunk0, partials, a, 0, sm);
+    dQd = agent_sum(agent_chunk0, partials, a, 1, sm);
+  }
   if (threadIdx.x != 0) return;
   double *s = scal + a * NS;
-  const double f1 = s[S_F1], f2 = s[S_F2];
+  const double f1 = s[S_F1];
+  // f(x2) - f(x1) = <egrad(x1), d> + 0.5 <d Q, d> for the quadratic cost: no cancellation
+  // between two costs of size 1e9 when the decrease is 1e-6
+  const double f2 = stable ? f1 + (dEG + 0.5 * dQd) : s[S_F2];
+  if (stable) s[S_F2] = f2;
   const double rho = (f1 - f2) / (-(eg + 0.5 * eh));
   s[S_RHO] = rho;
   double Delta = s[S_DELTA];
@@ -537,12 +547,19 @@ int rtr_solve_device(dcora_problem *p, double *x1, const dcora_ropt_params *prm,
     // ---- candidate, model decrease, rho (SolversTR::Run)
     DCORA_TRY(launch_retract(p, x1, eta, x2, prm->retraction, F_OUTER));
     DCORA_TRY(eval_f(p, x2, xq, S_F2, F_OUTER));  // xq = x2*Q, reused by the gradient
-    {
+    if (prm->stable_decrease) {
+      // d = x2 - x1 (t0), dQ = x2 Q - x1 Q = xq - (EG - G) (Hd); both vectors are free here
+      DCORA_TRY(launch_axpby(p, t0, -1, 1.0, x2, -1, -1.0, x1, F_OUTER));
+      DCORA_TRY(launch_axpby(p, Hd, -1, 1.0, xq, -1, -1.0, EG, F_OUTER));
+      if (p->has_G) DCORA_TRY(launch_axpby(p, Hd, -1, 1.0, Hd, -1, 1.0, p->G, F_OUTER));
+      const double *xs[4] = {t0, t0, eta, eta}, *ys[4] = {EG, Hd, gf, Heta};
+      DCORA_TRY(launch_dots(p, 4, xs, ys, F_OUTER));
+    } else {
       const double *xs[2] = {eta, eta}, *ys[2] = {gf, Heta};
       DCORA_TRY(launch_dots(p, 2, xs, ys, F_OUTER));
     }
     rtr_rho_kernel<<<nA, 128, 0, p->stream>>>(alist, M.agent_chunk0, p->partials, p->flags, p->scal,
-                                             single_mode);
+                                             single_mode, prm->stable_decrease ? 1 : 0);
     DCORA_LAUNCH_CHECK(p);
     pt.mark(4);
     DCORA_TRY(launch_copy(p, x1, x2, F_ACCEPT));

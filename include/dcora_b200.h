@@ -91,7 +91,11 @@ typedef struct {
   double RTR_initial_radius;  /* 100                                            */
   double time_bound_s;        /* 5.0 in the reference; <=0 disables             */
   int32_t retraction;         /* DCORA_RETRACT_QF / _POLAR                      */
-  int32_t reserved;
+  int32_t stable_decrease;    /* 0 (reference arithmetic): rho from f(x) - f(x+);
+                                 1: from <egrad(x), d> + 0.5 <d Q, d>, d = x+ - x -- the
+                                 same number without subtracting two large costs (an
+                                 agent's local cost can be 1e9 while the decrease RTR
+                                 tests is 1e-6)                                   */
 } dcora_ropt_params;
 
 /* ROPTResult (include/DCORA/DCORA_types.h:203-233), one per agent. */

@@ -226,3 +226,24 @@ def test_polar_retraction_in_the_solver():
     Xg = go.optimize(X0)
     assert rel_err(Xg, Xo) < 1e-7
     assert abs(go.getOptResult().fOpt - oo.result.fOpt) <= 1e-9 * abs(oo.result.fOpt)
+
+
+@pytest.mark.parametrize("name,r", [("smallGrid3D", 5), ("range_aided_slam_test_3d", 5), ("sphere2500", 4)])
+def test_stable_decrease_option_reaches_the_same_optimum(name, r):
+    # ROptParameters.stable_decrease: the trust-region ratio from <egrad, d> + 0.5 <dQ, d>
+    # (d = x+ - x) instead of f(x) - f(x+) -- the same number up to rounding, so the solve
+    # follows the same trajectory on well-scaled problems and ends at the same cost
+    import dcora_b200 as dc
+    P, g, info = central_problem(name, r)
+    gp = gpu_problem(P)
+    X0 = mf.random_point(P.L, np.random.default_rng(4))
+    out = []
+    for stable in (False, True):
+        go = dc.QuadraticOptimizer(gp, _params(RTR_iterations=60, RTR_tCG_iterations=200,
+                                               gradnorm_tol=1e-6, stable_decrease=stable))
+        go.optimize(X0)
+        out.append(go.getOptResult())
+    a, b = out
+    assert abs(a.fOpt - b.fOpt) <= 1e-9 * abs(a.fOpt) + 1e-12
+    assert b.gradNormOpt < 1e-6 or b.outer_iterations == 60
+    assert abs(a.outer_iterations - b.outer_iterations) <= 2

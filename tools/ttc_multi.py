@@ -12,7 +12,7 @@ import numpy as np
 def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol=0.1, eta=1e-3,
         max_iters=1000, check_every=5, log=print, dist_rank=0, world=1, group=None, device=0,
         r_max=None, nesterov_blocks=None, restart_interval=30, certify_max_iters=400,
-        agent_tol=None, stall_checks=0, adaptive_restart=False):
+        agent_tol=None, stall_checks=0, adaptive_restart=False, stable_decrease=False):
     import dcora_b200 as dc
     from dcora_b200 import graph as pg, rbcd, synthetic
     from dcora_b200.staircase import rbcd_staircase
@@ -27,7 +27,8 @@ def run(grid, agents, rank=5, range_fraction=0.1, seed=0, acc=True, gradnorm_tol
     if agent_tol is None:
         agent_tol = min(1e-2, 0.5 * gradnorm_tol / np.sqrt(agents))
     S = rbcd.RBCD(gp, rank, rank=dist_rank, world=world, device=device, group=group,
-                  params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=agent_tol), acceleration=acc,
+                  params=dc.ROptParameters(time_bound_s=0.0, gradnorm_tol=agent_tol,
+                                           stable_decrease=stable_decrease), acceleration=acc,
                   nesterov_blocks=nesterov_blocks, restart_interval=restart_interval)
     t2 = time.perf_counter()
     res = rbcd_staircase(S, X0, r_max=r_max or rank + 3, eta=eta, gradnorm_tol=gradnorm_tol,
@@ -60,6 +61,7 @@ if __name__ == "__main__":
     ap.add_argument("--certify-max-iters", type=int, default=400)
     ap.add_argument("--stall-checks", type=int, default=0)
     ap.add_argument("--adaptive-restart", action="store_true")
+    ap.add_argument("--stable-decrease", action="store_true")
     ap.add_argument("--range-fraction", type=float, default=0.1,
                     help="0: pose graph only (the synthetic stand-in of the absent g2o100k, configs[3])")
     a = ap.parse_args()
@@ -76,7 +78,7 @@ if __name__ == "__main__":
               nesterov_blocks=a.nesterov_blocks,
               restart_interval=a.restart_interval if a.restart_interval == "auto" else int(a.restart_interval),
               certify_max_iters=a.certify_max_iters, stall_checks=a.stall_checks,
-              adaptive_restart=a.adaptive_restart)
+              adaptive_restart=a.adaptive_restart, stable_decrease=a.stable_decrease)
     if rk == 0:
         print(json.dumps(out))
     if world > 1:
