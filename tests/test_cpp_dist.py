@@ -19,12 +19,12 @@ def bins():
     return exes
 
 
-def _dataset(tmp_path, S=5, robots=6, seed=3):
+def _dataset(tmp_path, S=5, robots=6, seed=3, range_fraction=0.15):
     """A noisy range-aided grid written as PyFG and read back by the ORACLE's reader; the
     product's GlobalProblem is built from what the oracle read."""
     from dcora_b200 import graph as pg, synthetic
     from oracle import dataio
-    meas, gt, idx = synthetic.grid3d(S, 0.15, seed=seed)
+    meas, gt, idx = synthetic.grid3d(S, range_fraction, seed=seed)
     part = pg.Partition.contiguous(meas.n, robots)
     path = str(tmp_path / f"grid{S}_{robots}.pyfg")
     write_pyfg(path, meas, part, gt=gt)
@@ -36,10 +36,12 @@ def _dataset(tmp_path, S=5, robots=6, seed=3):
     return path, gp, (meas, gt, idx)
 
 
+@pytest.mark.parametrize("range_fraction", [0.15, 0.0], ids=["range-aided", "pose-graph"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_cpp_pyfg_reader_partition_and_plans_match_python(bins, tmp_path, world):
+def test_cpp_pyfg_reader_partition_and_plans_match_python(bins, tmp_path, world, range_fraction):
     from dcora_b200 import rbcd
-    path, gp, _ = _dataset(tmp_path)
+    path, gp, _ = _dataset(tmp_path, range_fraction=range_fraction)
+    assert gp.ra == (range_fraction > 0)
     out = subprocess.run([bins["check_pyfg_partition"], path, str(world)], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr
