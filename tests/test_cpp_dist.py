@@ -101,3 +101,39 @@ def test_cpp_rbcd_host_matches_python_driver(bins, tmp_path, ranks, acc):
         assert abs(hist[it]["gradnorm"] - gn) <= 1e-6 * gn
     Xp = G.get_X()
     assert np.linalg.norm(Xc - Xp) <= 1e-7 * np.linalg.norm(Xp)
+
+
+@pytest.mark.parametrize("name", ["range_aided_slam_test_2d", "range_aided_slam_test_3d"])
+@pytest.mark.parametrize("world", [1, 2])
+def test_cpp_reader_on_the_reference_fixtures_with_landmarks(bins, tmp_path, name, world):
+    # the reference's 2-robot range-aided fixtures (poses, landmarks LA0 / LB0, ranges to poses
+    # and to landmarks; 2-D: VERTEX_SE2 / EDGE_SE2 lines) re-written as PyFG from the golden
+    # arrays and read by the C++ reader: same partitioned data matrices and plans as Python
+    from dcora_b200 import graph as pg, rbcd
+    from oracle import dataio
+    from tests.common import load_golden
+    meas, info = load_golden(name, prefix="local_")
+    M, part = product_measurements(meas, 2)
+    path = str(tmp_path / (name + ".pyfg"))
+    write_pyfg(path, M, part)
+    ds = dataio.read_pyfg(path)
+    M2, part2 = product_measurements(ds.meas, 2)
+    gp = pg.GlobalProblem(M2, part2, ra=True)
+    out = subprocess.run([bins["check_pyfg_partition"], path, str(world)], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout.splitlines()[-1])
+    Q = gp.Q().tocoo()
+    fro = float(np.sqrt(np.sum(Q.data ** 2)))
+    chk = float(np.sum(Q.data * np.cos(0.001 * Q.row + 0.002 * Q.col)))
+    assert (got["d"], got["n"], got["b"], got["l"], got["K"], got["robots"]) == \
+        (gp.d, gp.meas.n, gp.meas.b, len(gp.meas.rg_i), gp.K, 2)
+    assert got["b"] == 2
+    assert abs(got["fro"] - fro) <= 1e-12 * fro and abs(got["checksum"] - chk) <= 1e-10 * fro
+    for p, g in zip(rbcd.make_plans(gp, world), got["plans"]):
+        C = p.coupling.tocoo()
+        cf = float(np.sqrt(np.sum(C.data ** 2)))
+        assert (g["a0"], g["a1"], g["K"]) == (p.a0, p.a1, p.K)
+        assert abs(g["coupling_fro"] - cf) <= 1e-12 * max(cf, 1.0)
+        if world > 1:
+            assert tuple(g["seg"]) == tuple(p.seg) and g["key_sum"] == int(np.sum(p.row_key))
