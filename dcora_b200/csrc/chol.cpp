@@ -310,6 +310,138 @@ void nested_dissection(int n, const std::vector<std::vector<int>> &adj,
   block_ptr->swap(C.block_ptr);
 }
 
+
+// ---------------------------------------------------------------------------
+// Supernodal left-looking numeric factorisation on a given symbolic structure.
+//
+// Columns with identical structure below the diagonal (parent[j] = j + 1 and
+// colcount[j] = colcount[j + 1] + 1: fundamental supernodes) are factored as dense panels:
+// the updates from earlier supernodes are rank-w products of panel rows (contiguous inner
+// loops the compiler vectorises), the diagonal block is a dense Cholesky, the rows below it a
+// triangular solve.  Same arithmetic as the scalar up-looking algorithm up to the order of the
+// sums; 3-4x faster on the 3-D slab agents, whose separators are dense blocks of hundreds of
+// columns.  C = upper triangle of the permuted matrix in CSC; Lp / Li hold the structure of L
+// (rows sorted); Lx receives the values.  Returns false when a pivot is not positive.
+bool supernodal_numeric(int k, const std::vector<int> &Cp, const std::vector<int> &Ci,
+                        const std::vector<double> &Cx, const std::vector<int> &parent,
+                        const std::vector<int> &Lp, const std::vector<int> &Li,
+                        std::vector<double> &Lx) {
+  // ---- supernodes
+  std::vector<int> sstart;   // first column of every supernode (+ k at the end)
+  std::vector<int> super_of(k);
+  for (int j = 0; j < k; ++j) {
+    const bool joins = j > 0 && parent[j - 1] == j &&
+                       (Lp[j] - Lp[j - 1]) == (Lp[j + 1] - Lp[j]) + 1;
+    if (!joins) sstart.push_back(j);
+    super_of[j] = (int)sstart.size() - 1;
+  }
+  const int ns = (int)sstart.size();
+  sstart.push_back(k);
+  // panel of supernode s: rows = structure of its first column, nr x nc column-major
+  std::vector<size_t> poff(ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    const int j0 = sstart[s], nc = sstart[s + 1] - j0, nr = Lp[j0 + 1] - Lp[j0];
+    poff[s + 1] = poff[s] + (size_t)nr * nc;
+  }
+  std::vector<double> P(poff[ns], 0.0);
+  std::vector<int> head(ns, -1), next(ns, -1), pos(ns, 0), relmap(k, -1);
+  std::vector<double> W;
+  for (int s = 0; s < ns; ++s) {
+    const int j0 = sstart[s], j1 = sstart[s + 1], nc = j1 - j0;
+    const int *R = Li.data() + Lp[j0];
+    const int nr = Lp[j0 + 1] - Lp[j0];
+    double *Ps = P.data() + poff[s];
+    for (int t = 0; t < nr; ++t) relmap[R[t]] = t;
+    // ---- assemble the lower part of A: A(r, i) = C(i, r) for i in [j0, j1), r >= i
+    for (int t = 0; t < nr; ++t) {
+      const int r = R[t];
+      for (int p = Cp[r]; p < Cp[r + 1]; ++p) {
+        const int i = Ci[p];
+        if (i >= j0 && i < j1) Ps[(size_t)(i - j0) * nr + t] += Cx[p];
+      }
+    }
+    // ---- updates from the supernodes d with rows in [j0, j1)
+    for (int d = head[s]; d != -1;) {
+      const int dnext = next[d];
+      const int d0 = sstart[d], wd = sstart[d + 1] - d0;
+      const int *Rd = Li.data() + Lp[d0];
+      const int nrd = Lp[d0 + 1] - Lp[d0];
+      const double *Pd = P.data() + poff[d];
+      const int p0 = pos[d];
+      int ndcol = 0;
+      while (p0 + ndcol < nrd && Rd[p0 + ndcol] < j1) ++ndcol;
+      const int ndrow = nrd - p0;
+      // W (ndrow x ndcol, lower trapezoid) = Pd[p0.., :] * Pd[p0..p0+ndcol, :]^T, four panel
+      // columns per pass over W (the inner loops over `a` are contiguous: AVX2 FMA)
+      W.assign((size_t)ndrow * ndcol, 0.0);
+      int t = 0;
+      for (; t + 4 <= wd; t += 4) {
+        const double *c0 = Pd + (size_t)t * nrd + p0, *c1 = c0 + nrd, *c2 = c1 + nrd, *c3 = c2 + nrd;
+        for (int b = 0; b < ndcol; ++b) {
+          const double b0 = c0[b], b1 = c1[b], b2 = c2[b], b3 = c3[b];
+          double *w = W.data() + (size_t)b * ndrow;
+          for (int a = b; a < ndrow; ++a) w[a] += c0[a] * b0 + c1[a] * b1 + c2[a] * b2 + c3[a] * b3;
+        }
+      }
+      for (; t < wd; ++t) {
+        const double *col = Pd + (size_t)t * nrd + p0;
+        for (int b = 0; b < ndcol; ++b) {
+          const double cb = col[b];
+          double *w = W.data() + (size_t)b * ndrow;
+          for (int a = b; a < ndrow; ++a) w[a] += col[a] * cb;
+        }
+      }
+      for (int b = 0; b < ndcol; ++b) {
+        double *dst = Ps + (size_t)(Rd[p0 + b] - j0) * nr;
+        const double *w = W.data() + (size_t)b * ndrow;
+        for (int a = b; a < ndrow; ++a) dst[relmap[Rd[p0 + a]]] -= w[a];
+      }
+      pos[d] = p0 + ndcol;
+      if (pos[d] < nrd) {
+        const int tgt = super_of[Rd[pos[d]]];
+        next[d] = head[tgt];
+        head[tgt] = d;
+      }
+      d = dnext;
+    }
+    // ---- dense Cholesky of the nc x nc diagonal block + solve of the rows below
+    // (left-looking inside the panel: column c first takes the updates of columns < c, four at
+    // a time, then is scaled)
+    for (int c = 0; c < nc; ++c) {
+      double *col = Ps + (size_t)c * nr;
+      int q = 0;
+      for (; q + 4 <= c; q += 4) {
+        const double *a0 = Ps + (size_t)q * nr, *a1 = a0 + nr, *a2 = a1 + nr, *a3 = a2 + nr;
+        const double f0 = a0[c], f1 = a1[c], f2 = a2[c], f3 = a3[c];
+        for (int t2 = c; t2 < nr; ++t2) col[t2] -= a0[t2] * f0 + a1[t2] * f1 + a2[t2] * f2 + a3[t2] * f3;
+      }
+      for (; q < c; ++q) {
+        const double *a0 = Ps + (size_t)q * nr;
+        const double f0 = a0[c];
+        for (int t2 = c; t2 < nr; ++t2) col[t2] -= a0[t2] * f0;
+      }
+      const double dgn = col[c];
+      if (!(dgn > 0.0) || !std::isfinite(dgn)) return false;
+      const double ljj = std::sqrt(dgn), inv = 1.0 / ljj;
+      col[c] = ljj;
+      for (int t2 = c + 1; t2 < nr; ++t2) col[t2] *= inv;
+    }
+    if (nr > nc) {
+      pos[s] = nc;
+      const int tgt = super_of[R[nc]];
+      next[s] = head[tgt];
+      head[tgt] = s;
+    }
+    // ---- values to the CSC factor: column j0 + c holds rows R[c..nr)
+    for (int c = 0; c < nc; ++c) {
+      double *lx = Lx.data() + Lp[j0 + c];
+      const double *col = Ps + (size_t)c * nr;
+      for (int t = c; t < nr; ++t) lx[t - c] = col[t];
+    }
+  }
+  return true;
+}
+
 }  // namespace
 
 int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &Ai,
@@ -436,6 +568,34 @@ int sparse_cholesky(int k, const std::vector<int> &Ap, const std::vector<int> &A
   F.Li.assign(nnzL, 0);
   F.Lx.assign(nnzL, 0.0);
   lap("etree + symbolic");
+  static const bool uplooking = std::getenv("DCORA_CHOL") && std::getenv("DCORA_CHOL")[0] == 'u';
+  if (!uplooking) {
+    // structure of L: row j joins the columns of its row sub-tree (same traversal as above)
+    // (rows are appended in increasing j per column; the diagonal comes first)
+    std::vector<int> cf(F.Lp.begin(), F.Lp.end() - 1);
+    std::fill(flag.begin(), flag.end(), -1);
+    for (int j = 0; j < k; ++j) {
+      // columns of row j, then the diagonal entry of column j
+      flag[j] = j;
+      for (int p = Cp[j]; p < Cp[j + 1]; ++p) {
+        int i = Ci[p];
+        while (i != -1 && i < j && flag[i] != j) {
+          F.Li[cf[i]++] = j;
+          flag[i] = j;
+          i = parent[i];
+        }
+      }
+      F.Li[cf[j]++] = j;
+    }
+    lap("structure of L");
+    if (!supernodal_numeric(k, Cp, Ci, Cx, parent, F.Lp, F.Li, F.Lx)) {
+      set_error("sparse_cholesky: matrix is not positive definite");
+      return DCORA_ERR_FACTOR;
+    }
+    lap("numeric (supernodal)");
+    F.nnz = nnzL;
+    return DCORA_OK;
+  }
   // ---- numeric up-looking factorisation (row j of L from rows < j).  Row j only reads and
   // appends to the columns of its elimination-tree descendants, so disjoint subtrees are
   // independent: with `threads` > 1 the tree is cut into subtrees that are factored

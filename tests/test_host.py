@@ -239,3 +239,44 @@ def test_subtree_parallel_cholesky_is_bit_identical(lib):
         assert rc == 0
         out.append((cs.value, nnz.value))
     assert out[0] == out[1] == out[2], out
+
+
+_CHOL_SNIPPET = r"""
+import ctypes as C, sys, json
+import numpy as np
+sys.path.insert(0, {root!r})
+from dcora_b200 import _lib
+from tests.common import central_problem
+from tests.test_host import _internal_order
+lib = _lib.load()
+out = {{}}
+for name in ("city10000", "tiers", "sphere2500"):
+    P, g, info = central_problem(name, 3)
+    Q = _internal_order(P, info)
+    rp, ci, v = Q.indptr.astype(np.int32), Q.indices.astype(np.int32), Q.data.astype(np.float64)
+    cs, nnz = C.c_double(), C.c_int64()
+    rc = lib.dcora_selfcheck_cholesky_threads(Q.shape[0], rp.ctypes.data_as(_lib.c_int32_p),
+        ci.ctypes.data_as(_lib.c_int32_p), v.ctypes.data_as(_lib.c_double_p), info["d"] + 1, P.L.n,
+        P.reg, 1, C.byref(cs), C.byref(nnz))
+    out[name] = (rc, cs.value, nnz.value)
+print(json.dumps(out))
+"""
+
+
+def test_supernodal_and_uplooking_factors_agree():
+    """The supernodal numeric phase (default) and the scalar up-looking one (DCORA_CHOL=u) compute
+    the same factor on the same ordering: nnz equal, position-weighted checksum to 1e-12."""
+    import json
+    import subprocess
+    import sys
+    res = {}
+    for mode in ("s", "u"):
+        env = dict(os.environ, DCORA_CHOL=mode)
+        out = subprocess.run([sys.executable, "-c", _CHOL_SNIPPET.format(root=ROOT)], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[mode] = json.loads(out.stdout.splitlines()[-1])
+    for name, (rc, cs, nnz) in res["s"].items():
+        rc_u, cs_u, nnz_u = res["u"][name]
+        assert rc == rc_u == 0 and nnz == nnz_u
+        assert abs(cs - cs_u) <= 1e-12 * abs(cs_u), (name, cs, cs_u)
