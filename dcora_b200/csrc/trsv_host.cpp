@@ -27,6 +27,9 @@
 // into rounds of 8 lane groups and dealt to the warps by longest-processing-
 // time; the cost model (AgentTape::crit_iters) is what DCORA_TAPE_STATS prints.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -128,6 +131,14 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
   // their sources allow; rows of <= split_min tiles stay whole
   const int split_min = env_int("DCORA_TAPE_SPLIT", 24);
   const int piece_min = std::max(1, env_int("DCORA_TAPE_PIECE", 12));
+  const bool timing = std::getenv("DCORA_CHOL_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[tape] %-26s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
   // ---- final block partition: ND blocks, split to at most TRSV_MAX_BLOCK rows
   std::vector<int> bp(1, 0);
   for (size_t b = 0; b + 1 < F.blk_ptr.size(); ++b) {
@@ -175,6 +186,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
       }
   }
 
+  lap("partition + row lists");
   // ---- inverted diagonal blocks (shared by both directions)
   std::vector<std::vector<double>> Dinv(nb);
   for (int b = 0; b < nb; ++b) invert_diag_block(F, bp[b], bp[b + 1], &Dinv[b]);
@@ -212,6 +224,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
   };
   const bool stats = getenv("DCORA_TAPE_STATS") != nullptr;
 
+  lap("inverted diagonal blocks");
   // ---- levels of the block DAG, forward (L) and backward (L^T)
   std::vector<int> lvl[2];
   int nlev[2] = {0, 0};
@@ -236,6 +249,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
   std::vector<std::vector<Task>> slots((size_t)std::max(1, nslots_all));
   std::vector<int64_t> slot_load(slots.size(), 0);
 
+  lap("levels");
   // ---- folded off-diagonal rows  Lp[i, B] = L[i, B] D_B  (dense from the block's first
   // column to the row's last non-zero column in B)
   struct RowPart { int blk, len; std::vector<double> v; };
@@ -297,6 +311,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
     if (i0 < ord.size()) emit(i0, ord.size(), last);
   };
 
+  lap("folded rows Lp");
   // ---- forward tasks:  T[C rows] -= Lp[C rows, B] T[B]
   for (int r = 0; r < k;) {
     const int nrows = F.pose_start[r] == r ? dh : 1;
@@ -409,6 +424,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
     }
   }
 
+  lap("tasks (fwd, bwd, mid)");
   // ---------------------------------------------------- pack every slot and emit
   for (size_t sl = 0; sl < slots.size(); ++sl) {
     std::vector<Task> &tasks = slots[sl];
@@ -557,6 +573,7 @@ int build_agent_tape(const HostFactor &F, int dh, int nwarps, int nwarps_total, 
       }
     }
   }
+  lap("packing + emission");
   return DCORA_OK;
 }
 
