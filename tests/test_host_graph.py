@@ -181,3 +181,29 @@ def test_chordal_initialisation_beats_the_spanning_tree_guess():
     B = Xc[:, gp.rot_cols(i)].transpose(1, 0, 2)
     assert np.allclose(np.einsum("nri,nrj->nij", B, B), np.eye(3), atol=1e-12)
     assert np.allclose(np.linalg.norm(Xc[:, gp.sphere_col(np.arange(len(meas.rg_i)))], axis=0), 1.0)
+
+
+@pytest.mark.parametrize("robots", [1, 4])
+def test_synthetic_grid_agent_matrices_match_the_oracle_graph(robots):
+    # configs[4]-shaped data (noisy 3-D grid + range edges, contiguous agents): the product's
+    # vectorised assembly (graph.py) against the oracle's per-measurement Graph
+    # (constructQuadraticCostTermRASLAM, src/Graph.cpp:824-1188) agent by agent
+    import scipy.sparse as sp
+    from oracle import graph as og
+    from tests.common import oracle_measurements
+    meas, gt, idx = synthetic.grid3d(6, 0.15, seed=3)
+    part = pg.Partition.contiguous(meas.n, robots)
+    gp = pg.GlobalProblem(meas, part)
+    om = oracle_measurements(gp.meas, part)
+    diag, cross = gp.split()
+    for a in range(robots):
+        g = og.Graph(a, 4, 3, ra=True).set_measurements(om)
+        Qo = g.quadratic_matrix()
+        rp, col, val = diag[a]
+        Qp = sp.csr_matrix((val, col, rp), shape=Qo.shape)
+        assert (g.n, g.l, g.b) == (int(gp.n_a[a]), int(gp.l_a[a]), int(gp.b_a[a]))
+        assert abs(Qo - Qp).max() <= 1e-12 * abs(Qo).max()
+    # and the blocks + the cross-agent part make up the global matrix
+    B = sp.block_diag([sp.csr_matrix((v, c, r), shape=(len(r) - 1, len(r) - 1))
+                       for (r, c, v) in (diag[a] for a in range(robots))]).tocsr()
+    assert abs(B + cross - gp.Q()).max() == 0.0
